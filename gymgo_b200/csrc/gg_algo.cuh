@@ -60,7 +60,7 @@ struct Geo {
     typedef typename WordOf<WB>::type W;
     static_assert(N_ >= 2 && RPL_MAX >= 1 && RPL * S <= WB && LPB <= 32, "unsupported board size");
 
-    static constexpr W row_bits() { return (W(1) << N) - 1; }
+    static GG_HD constexpr W row_bits() { return (W(1) << N) - 1; }
     static GG_HD W rows_mask(int rows) {
         W m = 0;
         for (int i = 0; i < RPL; ++i)
@@ -249,7 +249,10 @@ struct Algo {
         own = own | m;
         // neighbours of the move; "surrounded" is judged before captures (state_utils.py:220-221)
         const P nb = nbrs(o, m);
-        const bool hemmed = o.any_board(m) && !o.any_board(o.andnot(nb, opp));
+        // (collectives are never placed behind a short-circuit: every lane of the warp must reach them)
+        const bool placed = o.any_board(m);
+        const bool gap = o.any_board(o.andnot(nb, opp));
+        const bool hemmed = placed && !gap;
         P ko = o.zero();
         const P seeds = nb & opp;
         if (o.any(seeds)) {
@@ -258,7 +261,8 @@ struct Algo {
             const P alive = flood(o, grp & nbrs(o, empty), grp);   // ... that still has a liberty
             const P dead = o.andnot(grp, alive);
             opp = o.andnot(opp, dead);
-            ko = o.pick(hemmed && o.count2(dead) == 1, dead, o.zero());   // one group of one stone
+            const int ndead = o.count2(dead);
+            ko = o.pick(hemmed && ndead == 1, dead, o.zero());            // one group of one stone
         }
         // mask for the player who moves next (= opp colour), also recomputed on a pass (ko expires)
         const P new_invd = invalid_mask(o, opp, own, ko);

@@ -1,0 +1,661 @@
+// gg_kernels.cuh - sm_100a kernels of the batched Go engine (templates over the board geometry).
+//
+// Work decomposition: a board occupies LPB adjacent lanes of a warp (9x9: 3 lanes x
+// 3 rows in a uint32, 10 boards per warp; 19x19: 7 lanes x 3 rows in a uint64, 4 boards per warp), a CTA
+// owns a contiguous tile of BT boards:
+//   1. the tile's packed records are staged into shared memory with ONE bulk async copy (TMA,
+//      cp.async.bulk + mbarrier; SASS: UBLKCP) - coalesced by construction;
+//   2. every lane keeps its slice of the three bit-planes in registers and runs gg::Algo (floods are
+//      carry chains + neighbour shuffles, votes are ballots) - no shared-memory traffic in the rules;
+//   3. new records go back to shared memory and leave with one bulk async store;
+//   4. the dense [6,N,N] observation (what GoEnv.step returns) is produced from a per-tile bit stream in
+//      shared memory: each 16-byte store expands one nibble (f32) or 16 bits (u8) - fully coalesced
+//      128-bit stores, which is the HBM traffic that dominates the step.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gg_algo.cuh"
+
+namespace gg {
+
+enum { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_CHILDREN = 2 };
+enum { DT_U8 = 0, DT_F32 = 1, DT_F64 = 2, DT_NONE = -1 };
+
+struct StepArgs {
+    const uint32_t* rec_in;     // STEP/ROLLOUT: [B] records; CHILDREN: [B] parent records
+    uint32_t* rec_out;          // STEP/ROLLOUT: [B]; CHILDREN: [B*A] child records or NULL
+    const int32_t* actions_in;  // STEP
+    int32_t* actions_out;       // ROLLOUT
+    uint8_t* status;            // STEP: [B]; CHILDREN: [B] parent status
+    uint8_t* valid_out;         // CHILDREN: [B*A] or NULL
+    void* obs;                  // dense output or NULL
+    int obs_dtype;              // DT_U8 / DT_F32
+    uint8_t* done_out;          // [slots] or NULL
+    int32_t* areas_out;         // [slots][2] or NULL
+    float* reward_out;          // [slots] or NULL (GoEnv.reward epilogue)
+    int reward_mode;            // 1 real, 2 heuristic
+    float komi;
+    long long slots;            // boards (STEP/ROLLOUT) or B*A (CHILDREN)
+    uint32_t opts;
+    unsigned long long seed, board0, t;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GG_DONE;\n"
+        "bra GG_WAIT;\n"
+        "GG_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA bulk copy shared -> global
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------- device Ops policy for gg::Algo
+template <class G>
+struct DevOps {
+    typedef typename G::W W;
+    typedef W P;
+    static constexpr unsigned FULL = 0xffffffffu;
+    static constexpr unsigned GM = G::LPB >= 32 ? 0xffffffffu : ((1u << G::LPB) - 1u);
+    int j;            // my lane inside the board's lane group
+    unsigned gshift;  // first warp lane of my board's group
+    W fullmask;       // real points of my slice (0 for ghost lanes / boards past the end)
+
+    __device__ __forceinline__ void init(int lane, bool real) {
+        const int slot = lane / G::LPB;
+        const bool ghost = slot >= G::BPW;
+        gshift = ghost ? unsigned(G::BPW * G::LPB) : unsigned(slot * G::LPB);
+        j = lane - int(gshift);
+        fullmask = (!ghost && real) ? G::rows_mask(G::rows_in_lane(j)) : W(0);
+    }
+    __device__ __forceinline__ P zero() const { return W(0); }
+    __device__ __forceinline__ P full() const { return fullmask; }
+    __device__ __forceinline__ P andnot(P a, P b) const { return a & ~b; }
+    __device__ __forceinline__ P east(P x) const { return x << 1; }
+    __device__ __forceinline__ P west(P x) const { return x >> 1; }
+    __device__ __forceinline__ P south(P x) const {   // result[r] = x[r-1]
+        W r = 0;
+        if (G::RPL > 1) r = x << (G::S % G::WB);
+        if (G::LPB > 1) {
+            const W prev = __shfl_up_sync(FULL, x, 1);
+            if (j > 0) r |= prev >> ((G::RPL - 1) * G::S);
+        }
+        return r;
+    }
+    __device__ __forceinline__ P north(P x) const {   // result[r] = x[r+1]
+        W r = 0;
+        if (G::RPL > 1) r = x >> (G::S % G::WB);
+        if (G::LPB > 1) {
+            const W next = __shfl_down_sync(FULL, x, 1);
+            if (j < G::LPB - 1) r |= (next & G::row_bits()) << ((G::RPL - 1) * G::S);
+        }
+        return r;
+    }
+    __device__ __forceinline__ P rev(P x) const { return w_rev(x); }
+    __device__ __forceinline__ P hfill(P s, P m, P mrev) const { return w_hfill(s, m, mrev); }
+    __device__ __forceinline__ bool any(P x) const { return __any_sync(FULL, x != 0); }
+    __device__ __forceinline__ unsigned group_ballot(bool pred) const {
+        return (__ballot_sync(FULL, pred) >> gshift) & GM;
+    }
+    __device__ __forceinline__ bool any_board(P x) const {
+        if (G::LPB == 1) return x != 0;
+        return group_ballot(x != 0) != 0;
+    }
+    __device__ __forceinline__ int count2(P x) const {
+        const int c = w_popc(x);
+        if (G::LPB == 1) return c > 2 ? 2 : c;
+        const unsigned b1 = group_ballot(c >= 1), b2 = group_ballot(c >= 2);
+        return (b2 || __popc(b1) >= 2) ? 2 : (b1 ? 1 : 0);
+    }
+    __device__ __forceinline__ int popc(P x) const {
+        const int c = w_popc(x);
+        if (G::LPB == 1) return c;
+        int total = 0;
+#pragma unroll
+        for (int l = 0; l < G::LPB; ++l) total += __shfl_sync(FULL, c, int(gshift) + l);
+        return total;
+    }
+    __device__ __forceinline__ P lowest(P x) const {
+        const W low = x & (~x + 1);
+        if (G::LPB == 1) return low;
+        const unsigned nz = group_ballot(x != 0);
+        return (j == __ffs(int(nz)) - 1) ? low : W(0);
+    }
+    __device__ __forceinline__ P single(int pt) const {
+        const int r = pt / G::N, c = pt - r * G::N;
+        const int lj = r / G::RPL;
+        return lj == j ? W(1) << ((r - lj * G::RPL) * G::S + c) : W(0);
+    }
+    __device__ __forceinline__ P pick(bool c, P a, P b) const { return c ? a : b; }
+    __device__ __forceinline__ int kth_point(P x, int k) const {
+        const int c = w_popc(x);
+        int before = 0;
+        if (G::LPB > 1) {
+#pragma unroll
+            for (int l = 0; l < G::LPB; ++l) {
+                const int cl = __shfl_sync(FULL, c, int(gshift) + l);
+                if (l < j) before += cl;
+            }
+        }
+        const int kl = k - before;
+        const bool mine = kl >= 0 && kl < c;
+        int pt = -1;
+        if (mine) {
+            const int bit = w_select(x, kl);
+            const int row = bit / G::S;
+            pt = (j * G::RPL + row) * G::N + (bit - row * G::S);
+        }
+        if (G::LPB > 1) {
+            const unsigned owner = group_ballot(mine);
+            pt = __shfl_sync(FULL, pt, int(gshift) + (owner ? __ffs(int(owner)) - 1 : 0));
+        }
+        return pt;
+    }
+};
+
+// -------------------------------------------------------------------------- record word access
+template <class G>
+__device__ __forceinline__ typename G::W rec_word(const uint32_t* rec, int plane, int j) {
+    const uint32_t* p = rec + (plane * G::LPB + j) * G::WW;
+    if (G::WW == 1) return typename G::W(p[0]);
+    return typename G::W(*reinterpret_cast<const uint64_t*>(p));
+}
+template <class G>
+__device__ __forceinline__ void rec_word_store(uint32_t* rec, int plane, int j, typename G::W v) {
+    uint32_t* p = rec + (plane * G::LPB + j) * G::WW;
+    if (G::WW == 1) p[0] = uint32_t(v);
+    else *reinterpret_cast<uint64_t*>(p) = uint64_t(v);
+}
+
+// CTA shape: BT (boards per tile) must be a multiple of 8 so that every tile of the dense output starts
+// 16-byte aligned for both f32 and u8 (6*N*N is even).
+template <class G>
+struct Tile {
+    static constexpr int WPC = (G::BPW % 2 == 0) ? 4 : 8;
+    static constexpr int THREADS = WPC * 32;
+    static constexpr int BT = WPC * G::BPW;
+    static constexpr int DENSE = 6 * G::NP;                      // elements per board
+    static constexpr int STREAM_W32 = (BT * DENSE + 31) / 32 + 2;
+    static_assert(BT % 8 == 0, "tile must keep the dense output 16-byte aligned");
+};
+
+// --------------------------------------------------------------------- dense-observation bit stream
+__device__ __forceinline__ void stream_put32(uint32_t* s, int off, uint32_t v) {
+    if (v == 0) return;
+    const int w = off >> 5, sh = off & 31;
+    atomicOr(&s[w], v << sh);
+    if (sh != 0 && (v >> (32 - sh)) != 0) atomicOr(&s[w + 1], v >> (32 - sh));
+}
+__device__ __forceinline__ void stream_put(uint32_t* s, int off, uint32_t v) { stream_put32(s, off, v); }
+__device__ __forceinline__ void stream_put(uint32_t* s, int off, uint64_t v) {
+    stream_put32(s, off, uint32_t(v));
+    stream_put32(s, off + 32, uint32_t(v >> 32));
+}
+// drop the guard bits of my slice: RPL rows of N bits, row-major
+template <class G>
+__device__ __forceinline__ typename G::W compact_rows(typename G::W w) {
+    typename G::W out = 0;
+#pragma unroll
+    for (int i = 0; i < G::RPL; ++i) out |= ((w >> (i * G::S)) & G::row_bits()) << (i * G::N);
+    return out;
+}
+template <class G>
+__device__ __forceinline__ void stream_put_board(uint32_t* s_bits, int slot_local, int j, typename G::W black,
+                                                 typename G::W white, typename G::W invd, uint32_t flags) {
+    typedef typename G::W W;
+    const int rows = G::rows_in_lane(j);
+    if (rows == 0) return;
+    const int base = slot_local * Tile<G>::DENSE + j * G::RPL * G::N;
+    const W ones = (W(1) << (rows * G::N)) - 1;       // rows*N < word bits by construction
+    stream_put(s_bits, base + 0 * G::NP, compact_rows<G>(black));
+    stream_put(s_bits, base + 1 * G::NP, compact_rows<G>(white));
+    stream_put(s_bits, base + 2 * G::NP, (flags & FLAG_TURN) ? ones : W(0));
+    stream_put(s_bits, base + 3 * G::NP, compact_rows<G>(invd));
+    stream_put(s_bits, base + 4 * G::NP, (flags & FLAG_PASS) ? ones : W(0));
+    stream_put(s_bits, base + 5 * G::NP, (flags & FLAG_DONE) ? ones : W(0));
+}
+
+// Expand `elems` stream bits to f32 / u8 at `dst` (16-byte aligned) with 128-bit stores.
+__device__ __forceinline__ void emit_f32(const uint32_t* s_bits, int elems, float* dst, int tid, int nthreads) {
+    const int nq = elems >> 2;
+    float4* dst4 = reinterpret_cast<float4*>(dst);
+    for (int q = tid; q < nq; q += nthreads) {
+        const uint32_t nib = s_bits[q >> 3] >> ((q & 7) << 2);
+        float4 v;
+        v.x = __uint_as_float((nib & 1u) * 0x3f800000u);
+        v.y = __uint_as_float(((nib >> 1) & 1u) * 0x3f800000u);
+        v.z = __uint_as_float(((nib >> 2) & 1u) * 0x3f800000u);
+        v.w = __uint_as_float(((nib >> 3) & 1u) * 0x3f800000u);
+        __stcs(dst4 + q, v);
+    }
+    for (int e = (nq << 2) + tid; e < elems; e += nthreads)
+        dst[e] = ((s_bits[e >> 5] >> (e & 31)) & 1u) ? 1.0f : 0.0f;
+}
+__device__ __forceinline__ void emit_u8(const uint32_t* s_bits, int elems, uint8_t* dst, int tid, int nthreads) {
+    const int nq = elems >> 4;
+    uint4* dst4 = reinterpret_cast<uint4*>(dst);
+    for (int q = tid; q < nq; q += nthreads) {
+        const uint32_t h = s_bits[q >> 1] >> ((q & 1) << 4);
+        uint4 v;
+        v.x = ((h & 15u) * 0x00204081u) & 0x01010101u;          // 4 bits -> 4 bytes of 0/1
+        v.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+        v.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+        v.w = (((h >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+        __stcs(dst4 + q, v);
+    }
+    for (int e = (nq << 4) + tid; e < elems; e += nthreads) dst[e] = uint8_t((s_bits[e >> 5] >> (e & 31)) & 1u);
+}
+
+// =================================================================================================
+// The hot kernel: one ply for a tile of boards (STEP), fused reset+sample+ply (ROLLOUT), or one child
+// per (parent, action) slot (CHILDREN).
+// =================================================================================================
+template <class G, int MODE>
+__global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
+    typedef typename G::W W;
+    typedef Tile<G> T;
+    __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
+    __shared__ uint32_t s_bits[T::STREAM_W32];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile_base = (long long)blockIdx.x * T::BT;
+    const long long left = a.slots - tile_base;
+    const int nb = left < T::BT ? int(left) : T::BT;             // slots of this tile that exist
+    const bool want_obs = a.obs != nullptr;
+
+    if (MODE != MODE_CHILDREN) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+        }
+    }
+    if (want_obs)
+        for (int i = tid; i < T::STREAM_W32; i += T::THREADS) s_bits[i] = 0;
+    __syncthreads();
+    if (MODE != MODE_CHILDREN) {
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
+            bulk_g2s(s_rec, a.rec_in + tile_base * G::REC_W32, uint32_t(nb) * G::REC_BYTES, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    }
+
+    const int slot_in_warp = lane / G::LPB;
+    const int slot_local = warp * G::BPW + slot_in_warp;
+    const bool real = slot_in_warp < G::BPW && slot_local < nb;
+    const long long slot = tile_base + slot_local;
+    DevOps<G> o;
+    o.init(lane, real);
+    const int j = o.j;
+    const bool holder = real && G::rows_in_lane(j) > 0;          // lane owns words of the record
+    uint32_t* my_rec = s_rec + slot_local * G::REC_W32;
+
+    W black = 0, white = 0, invd = 0;
+    uint32_t flags = 0;
+    int action = G::NP;
+    long long parent = 0;
+    if (MODE == MODE_CHILDREN) {
+        if (real) {
+            parent = slot / G::A;
+            action = int(slot - parent * G::A);
+            const uint32_t* prec = a.rec_in + parent * G::REC_W32;
+            if (holder) {
+                black = rec_word<G>(prec, 0, j);
+                white = rec_word<G>(prec, 1, j);
+                invd = rec_word<G>(prec, 2, j);
+            }
+            flags = prec[G::FLAGS_IDX];
+        }
+    } else if (real) {
+        if (holder) {
+            black = rec_word<G>(my_rec, 0, j);
+            white = rec_word<G>(my_rec, 1, j);
+            invd = rec_word<G>(my_rec, 2, j);
+        }
+        flags = my_rec[G::FLAGS_IDX];
+        if (MODE == MODE_STEP) action = a.actions_in[slot];
+    }
+
+    uint32_t opts = a.opts;
+    bool child_valid = true;
+    if (MODE == MODE_ROLLOUT) {
+        if (flags & FLAG_DONE) {                                  // auto-reset (gogame.init_state)
+            black = white = invd = 0;
+            flags = 0;
+        }
+        const unsigned long long gb = a.board0 + (unsigned long long)slot;
+        const uint32_t rnd = philox4x32_10(uint32_t(gb), uint32_t(gb >> 32), uint32_t(a.t), uint32_t(a.t >> 32),
+                                           uint32_t(a.seed), uint32_t(a.seed >> 32));
+        action = Algo<DevOps<G>>::sample_action(o, G(), invd, rnd);
+        opts = 0;
+    }
+    if (MODE == MODE_CHILDREN) {
+        // gogame.valid_moves: everything is "valid" once the game has ended (gogame.py:155-156)
+        const bool hit = o.any_board(o.single(action < G::NP ? action : 0) & invd);   // collective: no short-circuit
+        const bool on_invd = action < G::NP && hit;
+        child_valid = real && ((flags & FLAG_DONE) || !on_invd);
+        if (!child_valid) action = -1;                            // refused below -> planes untouched
+        opts &= OPT_CANONICAL;
+    }
+
+    const int status = Algo<DevOps<G>>::step(o, G(), black, white, invd, flags, action, opts);
+
+    if (MODE == MODE_CHILDREN) {
+        if (status != ST_OK) {                                    // padded slot: all zeros
+            black = white = invd = 0;
+            flags = 0;
+            if (child_valid && a.status && j == 0) a.status[parent] = 1;   // reference would assert here
+        }
+        if (real && j == 0 && a.valid_out) a.valid_out[slot] = child_valid ? 1 : 0;
+    }
+    if (real && j == 0) {
+        if (MODE == MODE_STEP && a.status) a.status[slot] = uint8_t(status);
+        if (MODE == MODE_ROLLOUT && a.actions_out) a.actions_out[slot] = action;
+        if (a.done_out) a.done_out[slot] = (flags & FLAG_DONE) ? 1 : 0;
+    }
+    // Scoring epilogue (gogame.areas + GoEnv.reward).  REAL rewards need areas only on finished boards, so the
+    // two floods are skipped unless some board of this warp just ended (warp-uniform vote).
+    const bool over = (flags & FLAG_DONE) != 0;
+    const bool want_reward = a.reward_out != nullptr;
+    const bool need_areas = a.areas_out != nullptr || (want_reward && (a.reward_mode == 2 || __any_sync(0xffffffffu, over)));
+    if (need_areas) {
+        int ba, wa;
+        Algo<DevOps<G>>::areas(o, black, white, ba, wa);
+        if (real && j == 0) {
+            if (a.areas_out) {
+                a.areas_out[2 * slot] = ba;
+                a.areas_out[2 * slot + 1] = wa;
+            }
+            if (want_reward) {
+                const float diff = float(ba - wa) - a.komi;
+                float r;
+                if (a.reward_mode == 1) r = over ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+                else r = over ? (diff > 0.f ? float(G::NP) : -float(G::NP)) : diff;
+                a.reward_out[slot] = r;
+            }
+        }
+    } else if (want_reward && real && j == 0) {
+        a.reward_out[slot] = 0.f;
+    }
+
+    // new record -> shared tile (padding words: kept from the input for STEP/ROLLOUT, zeroed for CHILDREN)
+    if (holder) {
+        rec_word_store<G>(my_rec, 0, j, black);
+        rec_word_store<G>(my_rec, 1, j, white);
+        rec_word_store<G>(my_rec, 2, j, invd);
+    }
+    if (real && j == 0) {
+        my_rec[G::FLAGS_IDX] = flags;
+        if (MODE == MODE_CHILDREN)
+            for (int i = G::FLAGS_IDX + 1; i < G::REC_W32; ++i) my_rec[i] = 0;
+    }
+    if (want_obs && holder) stream_put_board<G>(s_bits, slot_local, j, black, white, invd, flags);
+    fence_proxy_async();            // generic-proxy writes to s_rec must be visible to the bulk store
+    __syncthreads();
+
+    if (a.rec_out && tid == 0) {
+        bulk_s2g(a.rec_out + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (want_obs) {
+        const int elems = nb * T::DENSE;
+        const long long ebase = tile_base * T::DENSE;
+        if (a.obs_dtype == DT_F32) emit_f32(s_bits, elems, static_cast<float*>(a.obs) + ebase, tid, T::THREADS);
+        else emit_u8(s_bits, elems, static_cast<uint8_t*>(a.obs) + ebase, tid, T::THREADS);
+    }
+    if (a.rec_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ warp-layout helper kernels
+template <class G>
+struct WarpSlot {
+    static constexpr int THREADS = 128;
+    static constexpr int BOARDS = (THREADS / 32) * G::BPW;
+};
+
+template <class G>
+__global__ void __launch_bounds__(WarpSlot<G>::THREADS) k_areas(const uint32_t* rec, long long batch, int32_t* out) {
+    typedef typename G::W W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot_in_warp = lane / G::LPB;
+    const long long b = (long long)blockIdx.x * WarpSlot<G>::BOARDS + warp * G::BPW + slot_in_warp;
+    const bool real = slot_in_warp < G::BPW && b < batch;
+    DevOps<G> o;
+    o.init(lane, real);
+    W black = 0, white = 0;
+    if (real && G::rows_in_lane(o.j) > 0) {
+        black = rec_word<G>(rec + b * G::REC_W32, 0, o.j);
+        white = rec_word<G>(rec + b * G::REC_W32, 1, o.j);
+    }
+    int ba, wa;
+    Algo<DevOps<G>>::areas(o, black, white, ba, wa);
+    if (real && o.j == 0) {
+        out[2 * b] = ba;
+        out[2 * b + 1] = wa;
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(WarpSlot<G>::THREADS)
+    k_sample(const uint32_t* rec, long long batch, unsigned long long seed, unsigned long long board0,
+             unsigned long long t, int32_t* actions) {
+    typedef typename G::W W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot_in_warp = lane / G::LPB;
+    const long long b = (long long)blockIdx.x * WarpSlot<G>::BOARDS + warp * G::BPW + slot_in_warp;
+    const bool real = slot_in_warp < G::BPW && b < batch;
+    DevOps<G> o;
+    o.init(lane, real);
+    W invd = 0;
+    if (real && G::rows_in_lane(o.j) > 0) invd = rec_word<G>(rec + b * G::REC_W32, 2, o.j);
+    const unsigned long long gb = board0 + (unsigned long long)b;
+    const uint32_t rnd = philox4x32_10(uint32_t(gb), uint32_t(gb >> 32), uint32_t(t), uint32_t(t >> 32), uint32_t(seed),
+                                       uint32_t(seed >> 32));
+    const int action = Algo<DevOps<G>>::sample_action(o, G(), invd, rnd);
+    if (real && o.j == 0) actions[b] = action;
+}
+
+// ------------------------------------------------------------------------------ codecs & misc
+template <class G, class T>
+__global__ void k_pack(const T* dense, long long batch, uint32_t* rec) {
+    // one thread per (board, unit): units 0..3*LPB-1 = plane words, unit 3*LPB = flags + padding
+    constexpr int UNITS = 3 * G::LPB + 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batch * UNITS) return;
+    const long long b = gid / UNITS;
+    const int u = int(gid - b * UNITS);
+    const T* st = dense + b * 6 * G::NP;
+    uint32_t* r = rec + b * G::REC_W32;
+    if (u < 3 * G::LPB) {
+        const int plane = u / G::LPB, j = u - plane * G::LPB;
+        const int ch = plane == 2 ? 3 : plane;
+        typename G::W w = 0;
+        const int rows = G::rows_in_lane(j);
+        for (int i = 0; i < rows; ++i)
+            for (int c = 0; c < G::N; ++c)
+                if (st[ch * G::NP + (j * G::RPL + i) * G::N + c] != T(0)) w |= typename G::W(1) << (i * G::S + c);
+        rec_word_store<G>(r, plane, j, w);
+    } else {
+        bool turn = false, pass = false, done = true;
+        for (int p = 0; p < G::NP; ++p) {
+            turn |= st[2 * G::NP + p] != T(0);
+            pass |= st[4 * G::NP + p] != T(0);
+            done &= st[5 * G::NP + p] != T(0);
+        }
+        r[G::FLAGS_IDX] = (turn ? FLAG_TURN : 0u) | (pass ? FLAG_PASS : 0u) | (done ? FLAG_DONE : 0u);
+        for (int i = G::FLAGS_IDX + 1; i < G::REC_W32; ++i) r[i] = 0;
+    }
+}
+
+template <class G, class T>
+__global__ void k_unpack(const uint32_t* rec, long long batch, T* dense) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * 6 * G::NP) return;
+    const long long b = e / (6 * G::NP);
+    const int rem = int(e - b * 6 * G::NP);
+    const int ch = rem / G::NP, pt = rem - ch * G::NP;
+    const uint32_t* r = rec + b * G::REC_W32;
+    bool v;
+    if (ch == 2) v = r[G::FLAGS_IDX] & FLAG_TURN;
+    else if (ch == 4) v = r[G::FLAGS_IDX] & FLAG_PASS;
+    else if (ch == 5) v = r[G::FLAGS_IDX] & FLAG_DONE;
+    else {
+        const int plane = ch == 3 ? 2 : ch;
+        const int row = pt / G::N, c = pt - row * G::N, j = row / G::RPL;
+        v = (rec_word<G>(r, plane, j) >> ((row - j * G::RPL) * G::S + c)) & 1;
+    }
+    dense[e] = v ? T(1) : T(0);
+}
+
+template <class G, class T>
+__global__ void k_valid(const uint32_t* rec, long long batch, int ended_quirk, T* out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * G::A) return;
+    const long long b = e / G::A;
+    const int act = int(e - b * G::A);
+    const uint32_t* r = rec + b * G::REC_W32;
+    bool ok = true;
+    if (act < G::NP && !(ended_quirk && (r[G::FLAGS_IDX] & FLAG_DONE))) {
+        const int row = act / G::N, c = act - row * G::N, j = row / G::RPL;
+        ok = !((rec_word<G>(r, 2, j) >> ((row - j * G::RPL) * G::S + c)) & 1);
+    }
+    out[e] = ok ? T(1) : T(0);
+}
+
+template <class G>
+__global__ void k_reset(uint32_t* rec, long long batch, const uint8_t* mask) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batch * G::REC_W32) return;
+    const long long b = gid / G::REC_W32;
+    if (mask == nullptr || mask[b]) rec[gid] = 0;
+}
+
+template <class G>
+__global__ void k_canonical(const uint32_t* in, uint32_t* out, long long batch) {
+    // one thread per board so that in-place use (in == out) is race-free
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const uint32_t* r = in + b * G::REC_W32;
+    uint32_t* w = out + b * G::REC_W32;
+    const uint32_t flags = r[G::FLAGS_IDX];
+    const bool swap = flags & FLAG_TURN;
+    for (int i = 0; i < G::PLANE_W32; ++i) {
+        const uint32_t bl = r[i], wh = r[i + G::PLANE_W32];
+        w[i] = swap ? wh : bl;
+        w[i + G::PLANE_W32] = swap ? bl : wh;
+    }
+    for (int i = 2 * G::PLANE_W32; i < G::REC_W32; ++i) w[i] = r[i];
+    w[G::FLAGS_IDX] = flags & ~uint32_t(FLAG_TURN);
+}
+
+// ------------------------------------------------------------------------------ launch table
+struct SizeVTable {
+    int n, rec_bytes, lpb, rpl, wordbits, bpw, tile_boards, tile_threads;
+    cudaError_t (*step)(const StepArgs&, int mode, cudaStream_t);
+    cudaError_t (*areas)(const uint32_t*, long long, int32_t*, cudaStream_t);
+    cudaError_t (*sample)(const uint32_t*, long long, unsigned long long, unsigned long long, unsigned long long, int32_t*,
+                          cudaStream_t);
+    cudaError_t (*pack)(const void*, int dtype, long long, uint32_t*, cudaStream_t);
+    cudaError_t (*unpack)(const uint32_t*, long long, int dtype, void*, cudaStream_t);
+    cudaError_t (*valid)(const uint32_t*, long long, int quirk, int dtype, void*, cudaStream_t);
+    cudaError_t (*reset)(uint32_t*, long long, const uint8_t*, cudaStream_t);
+    cudaError_t (*canonical)(const uint32_t*, uint32_t*, long long, cudaStream_t);
+};
+
+inline unsigned blocks_for(long long items, int per_block) { return unsigned((items + per_block - 1) / per_block); }
+
+template <class G>
+struct Launch {
+    static cudaError_t step(const StepArgs& a, int mode, cudaStream_t s) {
+        if (a.slots <= 0) return cudaSuccess;
+        const unsigned grid = blocks_for(a.slots, Tile<G>::BT);
+        if (mode == MODE_STEP) k_step<G, MODE_STEP><<<grid, Tile<G>::THREADS, 0, s>>>(a);
+        else if (mode == MODE_ROLLOUT) k_step<G, MODE_ROLLOUT><<<grid, Tile<G>::THREADS, 0, s>>>(a);
+        else k_step<G, MODE_CHILDREN><<<grid, Tile<G>::THREADS, 0, s>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t areas(const uint32_t* rec, long long batch, int32_t* out, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        k_areas<G><<<blocks_for(batch, WarpSlot<G>::BOARDS), WarpSlot<G>::THREADS, 0, s>>>(rec, batch, out);
+        return cudaGetLastError();
+    }
+    static cudaError_t sample(const uint32_t* rec, long long batch, unsigned long long seed, unsigned long long board0,
+                              unsigned long long t, int32_t* actions, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        k_sample<G><<<blocks_for(batch, WarpSlot<G>::BOARDS), WarpSlot<G>::THREADS, 0, s>>>(rec, batch, seed, board0, t,
+                                                                                          actions);
+        return cudaGetLastError();
+    }
+    static cudaError_t pack(const void* dense, int dtype, long long batch, uint32_t* rec, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        const unsigned grid = blocks_for(batch * (3 * G::LPB + 1), 256);
+        if (dtype == DT_U8) k_pack<G, uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(dense), batch, rec);
+        else if (dtype == DT_F32) k_pack<G, float><<<grid, 256, 0, s>>>(static_cast<const float*>(dense), batch, rec);
+        else k_pack<G, double><<<grid, 256, 0, s>>>(static_cast<const double*>(dense), batch, rec);
+        return cudaGetLastError();
+    }
+    static cudaError_t unpack(const uint32_t* rec, long long batch, int dtype, void* dense, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        const unsigned grid = blocks_for(batch * 6 * G::NP, 256);
+        if (dtype == DT_U8) k_unpack<G, uint8_t><<<grid, 256, 0, s>>>(rec, batch, static_cast<uint8_t*>(dense));
+        else if (dtype == DT_F32) k_unpack<G, float><<<grid, 256, 0, s>>>(rec, batch, static_cast<float*>(dense));
+        else k_unpack<G, double><<<grid, 256, 0, s>>>(rec, batch, static_cast<double*>(dense));
+        return cudaGetLastError();
+    }
+    static cudaError_t valid(const uint32_t* rec, long long batch, int quirk, int dtype, void* out, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        const unsigned grid = blocks_for(batch * G::A, 256);
+        if (dtype == DT_U8) k_valid<G, uint8_t><<<grid, 256, 0, s>>>(rec, batch, quirk, static_cast<uint8_t*>(out));
+        else if (dtype == DT_F32) k_valid<G, float><<<grid, 256, 0, s>>>(rec, batch, quirk, static_cast<float*>(out));
+        else k_valid<G, double><<<grid, 256, 0, s>>>(rec, batch, quirk, static_cast<double*>(out));
+        return cudaGetLastError();
+    }
+    static cudaError_t reset(uint32_t* rec, long long batch, const uint8_t* mask, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        k_reset<G><<<blocks_for(batch * G::REC_W32, 256), 256, 0, s>>>(rec, batch, mask);
+        return cudaGetLastError();
+    }
+    static cudaError_t canonical(const uint32_t* in, uint32_t* out, long long batch, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        k_canonical<G><<<blocks_for(batch, 128), 128, 0, s>>>(in, out, batch);
+        return cudaGetLastError();
+    }
+    static constexpr SizeVTable table() {
+        return SizeVTable{G::N, G::REC_BYTES, G::LPB, G::RPL, G::WB, G::BPW, Tile<G>::BT, Tile<G>::THREADS,
+                          &step, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical};
+    }
+};
+
+}  // namespace gg

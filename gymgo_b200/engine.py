@@ -1,0 +1,210 @@
+"""Tensor-level host API over the C ABI: PyTorch owns the device memory and the stream, the kernels in
+libgymgo_b200.so do the work.  `GoEngine` is stateless (records in, records out); `BatchedGoEnv`
+(gymgo_b200/envs/batched_env.py) keeps one packed tensor of boards.
+
+Everything here requires a CUDA device - there is no CPU execution path."""
+import threading
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_TORCH2GG = {torch.uint8: _cabi.GG_U8, torch.float32: _cabi.GG_F32, torch.float64: _cabi.GG_F64}
+_tls = threading.local()
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _cabi.GymGoB200Error("gymgo_b200 needs a CUDA device (sm_100a kernels); no CPU fallback exists")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class GoEngine(object):
+    """Kernels for boards of side `size` on one device."""
+
+    def __init__(self, size, device=None):
+        _require_cuda()
+        self.lib = _cabi.lib()
+        if not self.lib.gg_supported(int(size)):
+            raise _cabi.GymGoB200Error("board size %r not supported (2..19)" % (size,))
+        self.size = int(size)
+        self.points = self.size * self.size
+        self.actions = self.points + 1
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.GymGoB200Error("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.layout = _cabi.layout(self.size)
+        self.rec_bytes = self.layout["rec_bytes"]
+
+    # ------------------------------------------------------------------ plumbing
+    def _enter(self):
+        """make this engine's device current for torch's and the library's CUDA runtime; returns the stream"""
+        idx = self.device.index
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
+        if getattr(_tls, "device", None) != idx:
+            _cabi.check(self.lib.gg_set_device(idx))
+            _tls.device = idx
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check_rec(self, rec):
+        if rec.dtype != torch.uint8 or rec.dim() != 2 or rec.shape[1] != self.rec_bytes or not rec.is_contiguous() \
+                or rec.device != self.device:
+            raise ValueError("records must be a contiguous uint8 [B, %d] tensor on %s" % (self.rec_bytes, self.device))
+
+    def _actions(self, actions, batch):
+        a = torch.as_tensor(actions)
+        if a.dim() == 0:
+            a = a.reshape(1)
+        a = a.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        if a.shape != (batch,):
+            raise ValueError("actions must have shape [%d]" % batch)
+        return a
+
+    def empty(self, *shape, dtype=torch.uint8):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ state type
+    def new_records(self, batch):
+        """`batch` empty boards, black to move (gogame.batch_init_state, gogame.py:28-31)."""
+        return torch.zeros((int(batch), self.rec_bytes), dtype=torch.uint8, device=self.device)
+
+    def pack(self, dense):
+        """dense [B,6,N,N] (uint8/float32/float64, values 0/1) -> packed records."""
+        d = torch.as_tensor(dense)
+        if d.dtype not in _TORCH2GG:
+            d = d.to(torch.float32)
+        d = d.to(self.device).contiguous()
+        if d.dim() != 4 or tuple(d.shape[1:]) != (6, self.size, self.size):
+            raise ValueError("dense states must be [B,6,%d,%d]" % (self.size, self.size))
+        rec = self.empty((d.shape[0], self.rec_bytes))
+        s = self._enter()
+        _cabi.check(self.lib.gg_pack(_ptr(d), _TORCH2GG[d.dtype], d.shape[0], self.size, _ptr(rec), s))
+        return rec
+
+    def unpack(self, rec, dtype=torch.float32, out=None):
+        self._check_rec(rec)
+        if out is None:
+            out = self.empty((rec.shape[0], 6, self.size, self.size), dtype=dtype)
+        s = self._enter()
+        _cabi.check(self.lib.gg_unpack(_ptr(rec), rec.shape[0], self.size, _TORCH2GG[out.dtype], _ptr(out), s))
+        return out
+
+    def reset(self, rec, mask=None):
+        self._check_rec(rec)
+        if mask is not None:
+            mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        s = self._enter()
+        _cabi.check(self.lib.gg_reset(_ptr(rec), rec.shape[0], self.size, _ptr(mask), s))
+        return rec
+
+    # ------------------------------------------------------------------ the hot path
+    def step(self, rec, actions, out=None, canonical=False, refuse_done=False, obs=None, obs_dtype=None,
+             want_status=True, want_done=False, want_areas=False, reward_mode=0, komi=0.0):
+        """One ply per board.  Returns dict(rec, status, obs, done, areas, reward) of device tensors
+        (entries not asked for are None).  `out=rec` steps in place."""
+        self._check_rec(rec)
+        b = rec.shape[0]
+        a = self._actions(actions, b)
+        if out is None:
+            out = torch.empty_like(rec)
+        else:
+            self._check_rec(out)
+        if obs is None and obs_dtype is not None:
+            obs = self.empty((b, 6, self.size, self.size), dtype=obs_dtype)
+        status = self.empty((b,)) if want_status else None
+        done = self.empty((b,)) if want_done else None
+        areas = self.empty((b, 2), dtype=torch.int32) if want_areas else None
+        reward = self.empty((b,), dtype=torch.float32) if reward_mode else None
+        flags = (_cabi.GG_STEP_CANONICAL if canonical else 0) | (_cabi.GG_STEP_REFUSE_DONE if refuse_done else 0)
+        s = self._enter()
+        _cabi.check(self.lib.gg_step(_ptr(rec), _ptr(a), _ptr(out), _ptr(status), b, self.size, flags, _ptr(obs),
+                                     _TORCH2GG[obs.dtype] if obs is not None else 0, _ptr(done), _ptr(areas),
+                                     _ptr(reward), int(reward_mode), float(komi), s))
+        return dict(rec=out, status=status, obs=obs, done=done, areas=areas, reward=reward)
+
+    def rollout_step(self, rec, seed, board0, t, actions=None, obs=None, done=None, areas=None, reward=None,
+                     reward_mode=0, komi=0.0):
+        """Fused auto-reset + uniform-random-legal action + ply, in place on `rec`.  All outputs are optional
+        preallocated tensors (nothing is allocated here: this is the benchmark loop)."""
+        s = self._enter()
+        _cabi.check(self.lib.gg_rollout_step(_ptr(rec), rec.shape[0], self.size, int(seed), int(board0), int(t),
+                                             _ptr(actions), _ptr(obs), _TORCH2GG[obs.dtype] if obs is not None else 0,
+                                             _ptr(done), _ptr(areas), _ptr(reward), int(reward_mode), float(komi), s))
+
+    def sample_legal(self, rec, seed, board0, t):
+        self._check_rec(rec)
+        out = self.empty((rec.shape[0],), dtype=torch.int32)
+        s = self._enter()
+        _cabi.check(self.lib.gg_sample_legal(_ptr(rec), rec.shape[0], self.size, int(seed), int(board0), int(t),
+                                             _ptr(out), s))
+        return out
+
+    # ------------------------------------------------------------------ derived quantities
+    def valid_moves(self, rec, ended_quirk=False, dtype=torch.float32):
+        self._check_rec(rec)
+        out = self.empty((rec.shape[0], self.actions), dtype=dtype)
+        s = self._enter()
+        _cabi.check(self.lib.gg_valid_moves(_ptr(rec), rec.shape[0], self.size, int(bool(ended_quirk)),
+                                            _TORCH2GG[dtype], _ptr(out), s))
+        return out
+
+    def children(self, rec, canonical=False, obs_dtype=torch.float32, want_rec=True, want_obs=True):
+        """-> dict(rec [B,A,rec_bytes], obs [B,A,6,N,N], valid [B,A] uint8, status [B] uint8)."""
+        self._check_rec(rec)
+        b = rec.shape[0]
+        crec = self.empty((b, self.actions, self.rec_bytes)) if want_rec else None
+        cobs = self.empty((b, self.actions, 6, self.size, self.size), dtype=obs_dtype) if want_obs else None
+        valid = self.empty((b, self.actions))
+        status = self.empty((b,))
+        s = self._enter()
+        _cabi.check(self.lib.gg_children(_ptr(rec), b, self.size, _cabi.GG_STEP_CANONICAL if canonical else 0,
+                                         _ptr(crec), _ptr(cobs), _TORCH2GG[obs_dtype] if want_obs else 0,
+                                         _ptr(valid), _ptr(status), s))
+        return dict(rec=crec, obs=cobs, valid=valid, status=status)
+
+    def areas(self, rec):
+        self._check_rec(rec)
+        out = self.empty((rec.shape[0], 2), dtype=torch.int32)
+        s = self._enter()
+        _cabi.check(self.lib.gg_areas(_ptr(rec), rec.shape[0], self.size, _ptr(out), s))
+        return out
+
+    def canonical(self, rec, out=None):
+        self._check_rec(rec)
+        if out is None:
+            out = torch.empty_like(rec)
+        s = self._enter()
+        _cabi.check(self.lib.gg_canonical(_ptr(rec), _ptr(out), rec.shape[0], self.size, s))
+        return out
+
+    # flags word of every record as int32 [B]: bit0 turn, bit1 previous pass, bit2 game over
+    def flags(self, rec):
+        self._check_rec(rec)
+        off = 3 * self.layout["lanes_per_board"] * (self.layout["word_bits"] // 8)
+        return rec[:, off:off + 4].contiguous().view(torch.int32).reshape(-1)
+
+
+_ENGINES = {}
+
+
+def engine(size, device=None):
+    """cached GoEngine per (size, device)"""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    key = (int(size), dev.index)
+    if key not in _ENGINES:
+        _ENGINES[key] = GoEngine(size, dev)
+    return _ENGINES[key]
+
+
+def to_numpy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)

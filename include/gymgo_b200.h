@@ -1,0 +1,156 @@
+/*
+ * gymgo_b200.h - C ABI of the B200-native batched Go engine (libgymgo_b200.so).
+ *
+ * This is the drop-in boundary for GymGo's hot path.  The reference has no FFI: its seam is the
+ * module-level pure-function API of gym_go/gogame.py that GoEnv reaches through `GoEnv.gogame`
+ * (gym_go/envs/go_env.py:21-22).  Each entry point below names the reference function(s) it replaces;
+ * the Python binding a maintainer would add is gymgo_b200/_cabi.py (ctypes), shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Plain C types only.  Every pointer is a DEVICE pointer into memory owned by the caller (e.g.
+ *     torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as void*.  Record and dense buffers
+ *     must be 16-byte aligned.  No allocation, no global state, no host synchronisation inside: calls
+ *     only enqueue kernels on `stream` and are re-entrant.
+ *   - Return value: GG_OK (0) or a negative GG_E* code (argument errors are detected before launch;
+ *     launch failures map to GG_ECUDA, cudaGetLastError text via gg_last_cuda_error()).
+ *   - Boards are independent.  Rule violations cannot raise on the device, so they are reported per
+ *     board in a `status` array (GG_ST_*), and a refused board's record is left unchanged - the
+ *     counterpart of the reference's AssertionError (gym_go/gogame.py:59, go_env.py:54-57).
+ *   - Packed record (one per board, `rec_bytes` from gg_layout, a multiple of 16):
+ *       three bit-planes [black | white | invalid-for-player-to-move], each `lanes_per_board` words of
+ *       `word_bits` bits; word j holds rows j*rows_per_lane ..., row r at bit (r % rows_per_lane)*(N+1),
+ *       column c at +c, bit N of every row slot is a zero guard bit;
+ *       then one uint32 flags word: bit0 turn (1 = white to move), bit1 previous move was a pass,
+ *       bit2 game over; zero padding to the 16-byte multiple.
+ *     It carries exactly the information of the reference's float64 [6,N,N] state (gogame.py:7-19).
+ *   - Dense state/observation tensors are [B,6,N,N] C-contiguous with values 0/1 in `dtype`.
+ */
+#ifndef GYMGO_B200_H
+#define GYMGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define GG_API __attribute__((visibility("default")))
+#else
+#define GG_API
+#endif
+
+/* return codes */
+#define GG_OK 0
+#define GG_EINVAL (-1)  /* bad argument (null pointer, negative batch, unknown dtype/flag) */
+#define GG_ESIZE (-2)   /* board size not supported by this build (see gg_supported) */
+#define GG_EALIGN (-3)  /* a record/dense pointer is not 16-byte aligned */
+#define GG_ECUDA (-4)   /* kernel launch failed; see gg_last_cuda_error() */
+
+/* per-board status values */
+#define GG_ST_OK 0
+#define GG_ST_INVALID_MOVE 1 /* INVD bit set at the action (occupied, ko, suicide)  - gogame.py:59 */
+#define GG_ST_OUT_OF_RANGE 2 /* action not in [0, N*N]                              - go_env.py:56-57 */
+#define GG_ST_GAME_OVER 3    /* GG_STEP_REFUSE_DONE given and the board is finished - go_env.py:54 */
+
+/* element types of dense tensors */
+#define GG_U8 0
+#define GG_F32 1
+#define GG_F64 2 /* pack/unpack/valid_moves only (the reference's own dtype) */
+
+/* reward_mode of gg_step / gg_rollout_step (GoEnv.reward, go_env.py:128-149) */
+#define GG_REWARD_NONE 0
+#define GG_REWARD_REAL 1      /* game over ? sign(black - white - komi) : 0                       (:138-139) */
+#define GG_REWARD_HEURISTIC 2 /* game over ? (diff > 0 ? +N*N : -N*N) : diff = black-white-komi   (:141-147) */
+
+/* gg_step / gg_children option bits */
+#define GG_STEP_CANONICAL 1u   /* canonical=True of gogame.next_state (gogame.py:83-85, :313-321) */
+#define GG_STEP_REFUSE_DONE 2u /* GoEnv.step's `assert not self.done` (go_env.py:54) */
+
+GG_API int gg_version(void);
+GG_API const char *gg_last_cuda_error(void);
+
+/* 1 if boards of side n are supported (this build: 2..19), else 0. */
+GG_API int gg_supported(int n);
+
+/* Bind the calling thread to CUDA device `ordinal` (cudaSetDevice).  The library carries its own
+ * statically linked CUDA runtime; call this when the caller's current device is not 0 (the Python
+ * binding does it from the tensors' device). */
+GG_API int gg_set_device(int ordinal);
+
+/* Geometry of the packed record for side n.  Any out pointer may be NULL.
+ * Replaces: the state type, gogame.init_state / batch_init_state (gogame.py:22-31), govars.py:4-11. */
+GG_API int gg_layout(int n, int *rec_bytes, int *lanes_per_board, int *rows_per_lane, int *word_bits);
+
+/* dense [B,6,N,N] (dtype GG_U8/GG_F32/GG_F64) -> packed records.  turn = max of plane 2, pass = max of
+ * plane 4, done = plane 5 all ones, exactly how the reference reads them (gogame.py:241-246, :200-201,
+ * :208-214); stone/invalid bits are `value != 0`. */
+GG_API int gg_pack(const void *dense, int dtype, int64_t batch, int n, void *rec, void *stream);
+
+/* packed records -> dense [B,6,N,N] of dtype. */
+GG_API int gg_unpack(const void *rec, int64_t batch, int n, int dtype, void *dense, void *stream);
+
+/* Zero (= gogame.init_state) the records whose mask byte is non-zero; mask == NULL resets all.
+ * Replaces: GoEnv.reset (go_env.py:40-47). */
+GG_API int gg_reset(void *rec, int64_t batch, int n, const uint8_t *mask, void *stream);
+
+/* One ply on every board: THE hot path.
+ * Replaces: gogame.next_state / batch_next_states (gogame.py:34-150) with state_utils.adj_data,
+ * update_pieces, compute_invalid_moves, set_turn (state_utils.py:24-83, :159-180, :214-241).
+ *   rec_in, rec_out  packed records; may be the same buffer (in place)
+ *   actions          int32 [B], N*N = pass
+ *   status           uint8 [B] or NULL
+ *   flags            GG_STEP_* bits
+ *   obs_out          NULL, or dense [B,6,N,N] of obs_dtype (GG_U8 or GG_F32) receiving the new state -
+ *                    what GoEnv.step returns as the observation (go_env.py:64)
+ *   done_out         NULL, or uint8 [B]: game over after this ply (gogame.game_ended, gogame.py:208-214)
+ *   areas_out        NULL, or int32 [B,2] Tromp-Taylor (black, white) areas of the new state
+ *                    (gogame.areas, gogame.py:275-300)
+ *   reward_out       NULL, or float32 [B]: GoEnv.reward of the new state for reward_mode/komi, fused into
+ *                    the kernel epilogue (areas are only flooded when the mode needs them) */
+GG_API int gg_step(const void *rec_in, const int32_t *actions, void *rec_out, uint8_t *status, int64_t batch, int n,
+                   uint32_t flags, void *obs_out, int obs_dtype, uint8_t *done_out, int32_t *areas_out,
+                   float *reward_out, int reward_mode, float komi, void *stream);
+
+/* Fused rollout ply: finished boards are first reset (auto-reset), then every board draws a uniformly
+ * random valid action incl. pass (GoEnv.uniform_random_action, go_env.py:78-81) from Philox4x32-10
+ * keyed (seed; counter = global board index board0+b, ply t) and plays it - same outputs as gg_step plus
+ * the chosen actions.  Trajectories do not depend on how the batch is sharded over GPUs. */
+GG_API int gg_rollout_step(void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,
+                           int32_t *actions_out, void *obs_out, int obs_dtype, uint8_t *done_out, int32_t *areas_out,
+                           float *reward_out, int reward_mode, float komi, void *stream);
+
+/* The sampler alone (no reset, no step): actions_out[b] = uniformly random valid action of board b.
+ * Replaces: GoEnv.uniform_random_action / gogame.random_action (go_env.py:78-81, gogame.py:395-404). */
+GG_API int gg_sample_legal(const void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,
+                    int32_t *actions_out, void *stream);
+
+/* out [B, N*N+1] of dtype: 1 = valid, pass always valid.  ended_quirk != 0 reproduces the single-board
+ * gogame.valid_moves (all ones once the game has ended, gogame.py:153-161); 0 gives batch_valid_moves
+ * (gogame.py:164-172).  invalid_moves = 1 - this. */
+GG_API int gg_valid_moves(const void *rec, int64_t batch, int n, int ended_quirk, int dtype, void *out, void *stream);
+
+/* Full legal-move expansion: slot (b, a) = next_state(parent b, action a) for every valid a, zeros
+ * otherwise (padded=True of gogame.children, gogame.py:175-186).
+ *   child_rec   NULL or packed [B, A] records          valid   NULL or uint8 [B, A]
+ *   child_obs   NULL or dense [B, A, 6, N, N]           status  NULL or uint8 [B]: 1 if a "valid" action was
+ *               of obs_dtype (GG_U8/GG_F32)                     refused (finished parent with stones: the
+ *                                                               reference asserts there, gogame.py:117)
+ *   flags       GG_STEP_CANONICAL or 0 */
+GG_API int gg_children(const void *rec, int64_t batch, int n, uint32_t flags, void *child_rec, void *child_obs,
+                int obs_dtype, uint8_t *valid, uint8_t *status, void *stream);
+
+/* int32 [B,2] (black area, white area).  Replaces: gogame.areas / batch_areas (gogame.py:275-310);
+ * winning = sign(black - white - komi) is left to the caller (gogame.py:225-238). */
+GG_API int gg_areas(const void *rec, int64_t batch, int n, int32_t *out, void *stream);
+
+/* Canonical form: boards with white to move get their stone planes swapped and turn cleared.
+ * Replaces: gogame.canonical_form / batch_canonical_form (gogame.py:313-337). */
+GG_API int gg_canonical(const void *rec_in, void *rec_out, int64_t batch, int n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYMGO_B200_H */

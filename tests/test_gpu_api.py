@@ -1,0 +1,131 @@
+"""GPU tests of the reference-facing Python surface: GoEnv / gogame drop-ins replaying the reference's own
+test sequences (SURVEY.md Appendix B fixtures) and BASELINE.json configs[0] (7x7 GoEnv.step games)."""
+import numpy as np
+import pytest
+import torch
+
+import golden_io
+from oracle import gogame_np as og
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", golden_io.kat_cases(), ids=lambda c: c["name"])
+def test_goenv_kat(case):
+    import gymgo_b200
+    n = case["states"].shape[2]
+    env = gymgo_b200.make("gym_go:go-v0", size=n, komi=case["komi"], reward_method=case["method"])
+    st = env.reset()
+    assert st.dtype == np.float64 and np.array_equal(st, case["states"][0])
+    for i, a in enumerate(case["actions"]):
+        a = int(a)
+        move = None if a == n * n else ((a // n, a % n) if i % 2 else a)       # exercise all action formats
+        st, rew, done, info = env.step(move)
+        assert np.array_equal(st, case["states"][i + 1]), (case["name"], i)
+        assert float(rew) == case["rewards"][i]
+        assert isinstance(done, int) and done == case["dones"][i]
+        assert info["turn"] == case["turns"][i]
+        assert int(info["prev_player_passed"]) == case["prev_pass"][i]
+        assert np.array_equal(info["invalid_moves"], og.invalid_moves(case["states"][i + 1]))
+    if case["raises"] >= 0:
+        with pytest.raises(AssertionError):
+            env.step(case["raises"])
+        assert np.array_equal(env.state(), case["states"][-1])      # a refused move changes nothing
+
+
+def test_goenv_full_games_7x7():
+    """configs[0]: state-for-state equality of whole 7x7 games incl. rewards for both reward methods"""
+    from gymgo_b200.envs import GoEnv
+    for g in golden_io.env_games():
+        env = GoEnv(7, komi=g["komi"], reward_method=g["method"])
+        env.reset()
+        for i, a in enumerate(g["actions"]):
+            st, rew, done, _ = env.step(int(a))
+            assert np.array_equal(st, g["states"][i + 1])
+            assert float(rew) == g["rewards"][i]
+            assert done == g["dones"][i]
+        assert float(env.winning()) == g["winning"]
+        with pytest.raises(AssertionError):
+            env.step(None)
+
+
+def test_goenv_misc_surface():
+    from gymgo_b200.envs import GoEnv
+    env = GoEnv(5)
+    with pytest.raises(AssertionError):
+        env.step((5, 0))                                            # out of bounds (test_invalid_moves.py:19-24)
+    env.step((1, 1))
+    env.step(None)
+    assert env.turn() == 0 and env.prev_player_passed()
+    kids = env.children(canonical=True, padded=True)
+    assert kids.shape == (26, 6, 5, 5) and kids.dtype == np.float64
+    assert np.array_equal(kids, og.children(env.state(), canonical=True, padded=True))
+    assert np.array_equal(env.children(padded=False), og.children(env.state(), padded=False))
+    assert np.array_equal(env.canonical_state(), og.canonical_form(env.state()))
+    a = env.uniform_random_action()
+    assert env.valid_moves()[a] == 1
+    assert "Turn" in str(env)
+
+
+def test_gogame_functional_api_numpy_and_torch():
+    from gym_go import gogame, govars      # the reference's import path
+    S0, A, S1 = golden_io.transitions(9)
+    S0, A, S1 = S0[:200], A[:200], S1[:200]
+    keep = S0.copy()
+    out = gogame.batch_next_states(S0, A)
+    assert out.dtype == np.float64 and np.array_equal(out, S1) and np.array_equal(S0, keep)
+    assert np.array_equal(gogame.next_state(S0[3], int(A[3]), canonical=True), og.next_state(S0[3], int(A[3]), True))
+    with pytest.raises(AssertionError):
+        occupied = int(np.flatnonzero(S1[5][govars.INVD_CHNL].reshape(-1))[0])
+        gogame.next_state(S1[5], occupied)
+    assert np.array_equal(gogame.valid_moves(S1[7]), og.valid_moves(S1[7]))
+    assert np.array_equal(gogame.invalid_moves(S1[7]), og.invalid_moves(S1[7]))
+    assert np.array_equal(gogame.batch_valid_moves(S1), og.batch_valid_moves(S1))
+    assert np.array_equal(gogame.children(S1[9]), og.children(S1[9]))
+    assert tuple(gogame.areas(S1[11])) == tuple(og.areas(S1[11]))
+    b, w = gogame.batch_areas(S1)
+    ob, ow = og.batch_areas(S1)
+    assert np.array_equal(b, ob) and np.array_equal(w, ow)
+    assert gogame.winning(S1[11], 2.5) == og.winning(S1[11], 2.5)
+    assert np.array_equal(gogame.batch_canonical_form(S1), og.batch_canonical_form(S1))
+    assert gogame.turn(S1[0]) == og.turn(S1[0]) and gogame.game_ended(S1[0]) == 0
+    assert gogame.num_liberties(S1[20]) is not None and gogame.action_size(S1[0]) == 82
+    # torch tensors stay on the device
+    t = torch.from_numpy(S0).cuda().float()
+    tout = gogame.batch_next_states(t, torch.from_numpy(A).cuda())
+    assert tout.is_cuda and tout.dtype == torch.float32 and np.array_equal(tout.cpu().numpy(), S1.astype(np.float32))
+
+
+def test_batched_env_semantics():
+    from gymgo_b200.envs import BatchedGoEnv
+    env = BatchedGoEnv(64, 5, reward_method="heuristic", komi=0.5, strict=False)
+    ref = [og.EnvOracle(5, komi=0.5, reward_method="heuristic") for _ in range(64)]
+    rng = np.random.RandomState(0)
+    for t in range(60):
+        vm = env.valid_moves(dtype=torch.uint8).cpu().numpy()
+        acts = np.array([rng.choice(np.flatnonzero(vm[i])) for i in range(64)], dtype=np.int32)
+        live = np.array([not r.done for r in ref])
+        obs, rew, done, info = env.step(acts)
+        st = info["status"].cpu().numpy()
+        assert (st[~live] == 3).all() and (st[live] == 0).all()
+        for i in np.flatnonzero(live):
+            s, r, d, _ = ref[i].step(int(acts[i]))
+            assert np.array_equal(obs[i].cpu().numpy(), s.astype(np.float32))
+            assert float(rew[i]) == float(r) and int(done[i]) == int(d)
+    strict = BatchedGoEnv(4, 5, strict=True)
+    strict.step([0, 1, 2, 3])
+    with pytest.raises(AssertionError):
+        strict.step([0, 6, 7, 8])
+
+
+def test_batched_env_random_step_is_shard_invariant():
+    from gymgo_b200.envs import BatchedGoEnv
+    whole = BatchedGoEnv(96, 9, seed=5, board_offset=0, obs_dtype=torch.uint8)
+    lo = BatchedGoEnv(48, 9, seed=5, board_offset=0, obs_dtype=torch.uint8)
+    hi = BatchedGoEnv(48, 9, seed=5, board_offset=48, obs_dtype=torch.uint8)
+    for _ in range(150):
+        ow, _, _, aw = whole.random_step()
+        ol, _, _, al = lo.random_step()
+        oh, _, _, ah = hi.random_step()
+        assert torch.equal(ow[:48], ol) and torch.equal(ow[48:], oh)
+        assert torch.equal(aw[:48], al) and torch.equal(aw[48:], ah)
