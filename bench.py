@@ -119,9 +119,21 @@ def _cpu_worker(size, boards, warmup, steps, seed, barrier, out_q):
     out_q.put(time.time() - t0)
 
 
+def usable_cores():
+    """host threads this process may really use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
 def cpu_reference_run(size, boards_per_core, warmup, steps, cores=None):
     """every host core steps `boards_per_core` boards with the numpy/scipy port; -> (plies/s, cores, seconds)"""
-    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    cores = cores or usable_cores()
     ctx = mp.get_context("fork")
     barrier, q = ctx.Barrier(cores), ctx.Queue()
     procs = [ctx.Process(target=_cpu_worker, args=(size, boards_per_core, warmup, steps, 100 + i, barrier, q))
@@ -195,23 +207,23 @@ def run_ours(args, wl, rank, world, local_rank):
     # rotating observation buffers: > L2 (126 MB) in total so no step rewrites lines still in cache
     dense_bytes = boards * 6 * size * size * obs_elem
     nbuf = max(2, int(-(-300e6 // dense_bytes)))
-    obs = [eng.empty((boards, 6, size, size), dtype=obs_dtype) for _ in range(nbuf)]
+    obs_ring = eng.empty((nbuf, boards, 6, size, size), dtype=obs_dtype)
     rec = eng.new_records(boards)
     actions_log = torch.empty((W + K, boards), dtype=torch.int32, device=dev)
     reward = eng.empty((boards,), dtype=torch.float32)
     done = eng.empty((boards,))
 
-    def ply(t):
-        eng.rollout_step(rec, SEED, board0, t, actions=actions_log[t], obs=obs[t % nbuf], done=done, reward=reward,
-                         reward_mode=1, komi=0.0)
+    def plies(t0, count):
+        # ONE C call (gg_rollout) enqueues `count` launches of the fused kernel, one per ply, back to back
+        eng.rollout(rec, SEED, board0, t0, count, actions_log=actions_log[t0:], obs_ring=obs_ring, done=done,
+                    reward=reward, reward_mode=1, komi=0.0)
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    for t in range(W):
-        ply(t)
+    plies(0, W)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -221,8 +233,7 @@ def run_ours(args, wl, rank, world, local_rank):
     barrier()
     wall0 = time.time()
     ev0.record()
-    for t in range(W, W + K):
-        ply(t)
+    plies(W, K)
     ev1.record()
     barrier()
     wall1 = time.time()
@@ -302,13 +313,17 @@ def run_ours(args, wl, rank, world, local_rank):
                          "launch_us": launch_s * 1e6},
         }
         if world == 1 and not args.no_cpu_baseline:
-            bpc = 16 if size <= 9 else 8
+            # the CPU arm runs in a fresh interpreter (no CUDA context / torch thread pools to fork)
+            env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
             cpu_steps = 260 if size <= 9 else 220
-            v, cores, cs = cpu_reference_run(size, bpc, 20, cpu_steps)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d cores x %d boards x %d plies of the same policy through the numpy/scipy "
-                                              "port of gogame.next_state (%.1f s)" % (cores, bpc, cpu_steps, cs),
-                                    "c_oracle_1core": c_oracle_rate(size)}
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                                args.workload, "--steps", str(cpu_steps), "--warmup", "20"],
+                               stdout=subprocess.PIPE, text=True, env=env)
+            try:
+                ref = json.loads(p.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = dict(ref["cpu_baseline"], c_oracle_1core=c_oracle_rate(size))
+            except Exception as exc:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": repr(exc)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

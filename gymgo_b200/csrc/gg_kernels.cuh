@@ -247,17 +247,15 @@ __device__ __forceinline__ void stream_put_board(uint32_t* s_bits, int slot_loca
 }
 
 // Expand `elems` stream bits to f32 / u8 at `dst` (16-byte aligned) with 128-bit stores.
-__device__ __forceinline__ void emit_f32(const uint32_t* s_bits, int elems, float* dst, int tid, int nthreads) {
+// f32: one stream nibble -> one float4 through a 16-entry shared-memory table (1 LDS.128 instead of 12 ALU ops).
+__device__ __forceinline__ void emit_f32(const uint32_t* s_bits, const float4* s_lut, int elems, float* dst, int tid,
+                                         int nthreads) {
     const int nq = elems >> 2;
     float4* dst4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
     for (int q = tid; q < nq; q += nthreads) {
-        const uint32_t nib = s_bits[q >> 3] >> ((q & 7) << 2);
-        float4 v;
-        v.x = __uint_as_float((nib & 1u) * 0x3f800000u);
-        v.y = __uint_as_float(((nib >> 1) & 1u) * 0x3f800000u);
-        v.z = __uint_as_float(((nib >> 2) & 1u) * 0x3f800000u);
-        v.w = __uint_as_float(((nib >> 3) & 1u) * 0x3f800000u);
-        __stcs(dst4 + q, v);
+        const uint32_t nib = (s_bits[q >> 3] >> ((q & 7) << 2)) & 15u;
+        __stcs(dst4 + q, s_lut[nib]);
     }
     for (int e = (nq << 2) + tid; e < elems; e += nthreads)
         dst[e] = ((s_bits[e >> 5] >> (e & 31)) & 1u) ? 1.0f : 0.0f;
@@ -287,6 +285,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     typedef Tile<G> T;
     __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
     __shared__ uint32_t s_bits[T::STREAM_W32];
+    __shared__ __align__(16) float4 s_lut[16];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,8 +300,11 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
             fence_mbar_init();
         }
     }
-    if (want_obs)
+    if (want_obs) {
         for (int i = tid; i < T::STREAM_W32; i += T::THREADS) s_bits[i] = 0;
+        if (tid < 16)
+            s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    }
     __syncthreads();
     if (MODE != MODE_CHILDREN) {
         if (tid == 0) {
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     if (want_obs) {
         const int elems = nb * T::DENSE;
         const long long ebase = tile_base * T::DENSE;
-        if (a.obs_dtype == DT_F32) emit_f32(s_bits, elems, static_cast<float*>(a.obs) + ebase, tid, T::THREADS);
+        if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, elems, static_cast<float*>(a.obs) + ebase, tid, T::THREADS);
         else emit_u8(s_bits, elems, static_cast<uint8_t*>(a.obs) + ebase, tid, T::THREADS);
     }
     if (a.rec_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

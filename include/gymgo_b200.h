@@ -122,6 +122,14 @@ GG_API int gg_rollout_step(void *rec, int64_t batch, int n, uint64_t seed, uint6
                            int32_t *actions_out, void *obs_out, int obs_dtype, uint8_t *done_out, int32_t *areas_out,
                            float *reward_out, int reward_mode, float komi, void *stream);
 
+/* `steps` consecutive gg_rollout_step plies (t = t0 .. t0+steps-1) enqueued back to back from C, so a Python
+ * caller pays one call instead of one per ply.  Ply p writes its observation to slot (t0+p) % obs_ring of
+ * obs_ring_buf ([obs_ring, B, 6, N, N], may be NULL) and its actions to actions_log[p] ([steps, B], may be
+ * NULL); done_out / reward_out (may be NULL) hold the values of the last ply. */
+GG_API int gg_rollout(void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
+                      int32_t *actions_log, void *obs_ring_buf, int obs_dtype, int obs_ring, uint8_t *done_out,
+                      float *reward_out, int reward_mode, float komi, void *stream);
+
 /* The sampler alone (no reset, no step): actions_out[b] = uniformly random valid action of board b.
  * Replaces: GoEnv.uniform_random_action / gogame.random_action (go_env.py:78-81, gogame.py:395-404). */
 GG_API int gg_sample_legal(const void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,
