@@ -122,11 +122,25 @@ GG_HD int w_ctz(uint64_t x) {
     return __builtin_ctzll(x);
 #endif
 }
-// position of the k-th (0-based) set bit of x; requires k < popc(x)
-template <class W>
-GG_HD int w_select(W x, int k) {
-    for (int i = 0; i < k; ++i) x &= x - 1;
-    return w_ctz(x);
+// position of the k-th (0-based) set bit of x; requires k < popc(x).  Branch-light binary search on
+// popcounts of the low halves (5 / 6 rounds) instead of clearing k bits one by one.
+GG_HD int w_select(uint32_t x, int k) {
+    int pos = 0;
+#define GG_SEL_STEP(BITS)                                   \
+    {                                                       \
+        const int c = w_popc(uint32_t(x & ((1u << BITS) - 1u))); \
+        const bool up = k >= c;                             \
+        k -= up ? c : 0;                                    \
+        pos += up ? BITS : 0;                               \
+        x = up ? (x >> BITS) : x;                           \
+    }
+    GG_SEL_STEP(16) GG_SEL_STEP(8) GG_SEL_STEP(4) GG_SEL_STEP(2) GG_SEL_STEP(1)
+#undef GG_SEL_STEP
+    return pos;
+}
+GG_HD int w_select(uint64_t x, int k) {
+    const int c = w_popc(uint32_t(x));
+    return k >= c ? 32 + w_select(uint32_t(x >> 32), k - c) : w_select(uint32_t(x), k);
 }
 
 // Row flood inside one word: every maximal run of consecutive bits of `m` that contains a bit of
@@ -178,9 +192,8 @@ struct Algo {
         return (o.east(x) | o.west(x) | o.south(x) | o.north(x)) & o.full();
     }
 
-    // stones of `mask` 4-connected (inside mask) to `seed`; seed must be a subset of mask
-    static GG_HD P flood(const O& o, P seed, P mask) {
-        P mrev = o.rev(mask);
+    // stones of `mask` 4-connected (inside mask) to `seed`; seed must be a subset of mask; mrev = rev(mask)
+    static GG_HD P flood(const O& o, P seed, P mask, P mrev) {
         P x = seed;
         for (;;) {
             x = o.hfill(x, mask, mrev);
@@ -190,38 +203,52 @@ struct Algo {
         }
         return x;
     }
+    static GG_HD P flood(const O& o, P seed, P mask) { return flood(o, seed, mask, o.rev(mask)); }
 
     // INVD plane for the player whose stones are `nxt` (to move), `oth` = the player who just moved.
     // invalid(p) = occupied | ko | ( no empty neighbour
     //                                & not adjacent to an `oth` group with exactly one liberty
     //                                & not adjacent to a  `nxt` group with two or more liberties )
-    // Only "pockets" (empty points without an empty neighbour) can fall in the third class.  A group
-    // that owns a liberty which is NOT a pocket and touches a pocket has >= 2 liberties, so ONE flood
-    // per colour settles almost every group; the few groups whose liberties are all pockets are then
-    // visited one at a time.
+    // Only "pockets" (empty points without an empty neighbour) can fall in the third class, and only the
+    // groups next to them matter.  Most of those are settled without visiting them one by one:
+    //   * a group owning a liberty that is not a pocket, or a stone that touches two empty points, has
+    //     >= 2 liberties: ONE flood per colour ("big") finds all of them;
+    //   * of what is left every stone touches at most one empty point, so a stone without a same-coloured
+    //     neighbour is a one-stone group in atari: bit-parallel, no flood;
+    //   * the remaining groups (all their liberties are pockets) are flooded one per trip.
     static GG_HD P invalid_mask(const O& o, P nxt, P oth, P ko) {
         const P occ = nxt | oth;
         const P empty = o.andnot(o.full(), occ);
-        const P pockets = o.andnot(empty, nbrs(o, empty));
+        const P ee = o.east(empty), ew = o.west(empty), es = o.south(empty), en = o.north(empty);
+        const P pockets = o.andnot(empty, ee | ew | es | en);
         P bad = pockets;                               // pockets not yet shown to be playable
         if (o.any(pockets)) {
             const P open = o.andnot(empty, pockets);   // liberties that have an empty neighbour
-            const P touch_open = nbrs(o, open);
-            const P big_nxt = flood(o, nxt & touch_open, nxt);   // groups with a non-pocket liberty
-            const P big_oth = flood(o, oth & touch_open, oth);
+            const P two = (ee & ew) | (es & en) | ((ee | ew) & (es | en));   // touches >= 2 empty points
+            const P healthy = nbrs(o, open) | two;
+            const P big_nxt = flood(o, nxt & healthy, nxt);                // groups with >= 2 liberties (sufficient)
+            const P big_oth = flood(o, oth & healthy, oth);
             bad = o.andnot(bad, nbrs(o, big_nxt));     // own group with >= 2 liberties: safe
-            const P rest_nxt = o.andnot(nxt, big_nxt); // groups whose liberties are all pockets
+            const P rest_nxt = o.andnot(nxt, big_nxt);
             const P rest_oth = o.andnot(oth, big_oth);
-            P todo = (rest_nxt | rest_oth) & nbrs(o, bad);
-            while (o.any(todo)) {
-                const P s = o.lowest(todo);
-                const bool mine = o.any_board(s & nxt);
-                const P grp = flood(o, s, o.pick(mine, rest_nxt, rest_oth));
-                const P libs = nbrs(o, grp) & empty;
-                const int nl = o.count2(libs);
-                const bool playable = mine ? (nl >= 2) : (nl == 1);   // stays alive / captures
-                bad = o.andnot(bad, o.pick(playable, libs, o.zero()));
-                todo = o.andnot(todo, grp) & nbrs(o, bad);
+            if (o.any(bad)) {
+                const P adj = nbrs(o, bad);
+                const P cand_nxt = rest_nxt & adj, cand_oth = rest_oth & adj;
+                const P lone_nxt = o.andnot(cand_nxt, nbrs(o, nxt));       // one stone, one liberty: no help
+                const P lone_oth = o.andnot(cand_oth, nbrs(o, oth));       // one stone in atari: capturable
+                bad = o.andnot(bad, nbrs(o, lone_oth));
+                P todo = (o.andnot(cand_nxt, lone_nxt) | o.andnot(cand_oth, lone_oth)) & nbrs(o, bad);
+                const P rrev_nxt = o.rev(rest_nxt), rrev_oth = o.rev(rest_oth);
+                while (o.any(todo)) {
+                    const P s = o.lowest(todo);
+                    const bool mine = o.any_board(s & nxt);
+                    const P grp = flood(o, s, o.pick(mine, rest_nxt, rest_oth), o.pick(mine, rrev_nxt, rrev_oth));
+                    const P libs = nbrs(o, grp) & empty;
+                    const int nl = o.count2(libs);
+                    const bool playable = mine ? (nl >= 2) : (nl == 1);   // stays alive / captures
+                    bad = o.andnot(bad, o.pick(playable, libs, o.zero()));
+                    todo = o.andnot(todo, grp) & nbrs(o, bad);
+                }
             }
         }
         return occ | bad | ko;

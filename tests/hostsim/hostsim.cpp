@@ -12,6 +12,9 @@
 
 namespace {
 
+// developer statistics (single-threaded test code): loop trips of the algorithm on the current board
+static long g_stat_hfill = 0, g_stat_lowest = 0;
+
 template <class G>
 struct HostPlane {
     typename G::W w[G::LPB];
@@ -56,6 +59,7 @@ struct HostOps {
     }
     P rev(P x) const { for (int j = 0; j < G::LPB; ++j) x.w[j] = gg::w_rev(x.w[j]); return x; }
     P hfill(P s, const P& m, const P& mrev) const {
+        ++g_stat_hfill;
         for (int j = 0; j < G::LPB; ++j) s.w[j] = gg::w_hfill(s.w[j], m.w[j], mrev.w[j]);
         return s;
     }
@@ -64,6 +68,7 @@ struct HostOps {
     int popc(const P& x) const { int c = 0; for (int j = 0; j < G::LPB; ++j) c += gg::w_popc(x.w[j]); return c; }
     int count2(const P& x) const { int c = popc(x); return c > 2 ? 2 : c; }
     P lowest(const P& x) const {
+        ++g_stat_lowest;
         P y = zero();
         for (int j = 0; j < G::LPB; ++j)
             if (x.w[j]) { y.w[j] = x.w[j] & (~x.w[j] + 1); break; }
@@ -178,9 +183,11 @@ struct Sim {
         }
     }
     // one fused rollout step as the device kernel does it: reset finished boards, sample, step
-    static void rollout_step(uint32_t* recs, int batch, uint64_t seed, uint64_t board0, uint64_t t, int32_t* actions) {
+    static void rollout_step(uint32_t* recs, int batch, uint64_t seed, uint64_t board0, uint64_t t, int32_t* actions,
+                             int32_t* stats = nullptr) {
         HostOps<G> o;
         for (int b = 0; b < batch; ++b) {
+            g_stat_hfill = g_stat_lowest = 0;
             HostPlane<G> bl, wh, iv;
             uint32_t flags;
             uint32_t* rec = recs + size_t(b) * G::REC_W32;
@@ -192,6 +199,7 @@ struct Sim {
             int a = gg::Algo<HostOps<G>>::sample_action(o, G(), iv, rnd);
             gg::Algo<HostOps<G>>::step(o, G(), bl, wh, iv, flags, a, 0u);
             rec_store<G>(rec, bl, wh, iv, flags);
+            if (stats) { stats[2 * b] = int32_t(g_stat_hfill); stats[2 * b + 1] = int32_t(g_stat_lowest); }
             if (actions) actions[b] = a;
         }
     }
@@ -246,6 +254,16 @@ int hs_areas(int n, const uint32_t* in, int batch, int32_t* out) {
 int hs_rollout_step(int n, uint32_t* recs, int batch, uint64_t seed, uint64_t board0, uint64_t t, int32_t* actions) {
     switch (n) {
 #define X(NN) case NN: Sim<gg::Geo<NN>>::rollout_step(recs, batch, seed, board0, t, actions); return 0;
+        GG_FOR_SIZES(X)
+#undef X
+    }
+    return -1;
+}
+// developer statistics: stats[b] = {flood iterations, pocket-loop trips} of board b in this ply
+int hs_rollout_step_stats(int n, uint32_t* recs, int batch, uint64_t seed, uint64_t board0, uint64_t t, int32_t* actions,
+                          int32_t* stats) {
+    switch (n) {
+#define X(NN) case NN: Sim<gg::Geo<NN>>::rollout_step(recs, batch, seed, board0, t, actions, stats); return 0;
         GG_FOR_SIZES(X)
 #undef X
     }
