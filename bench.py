@@ -210,13 +210,13 @@ def run_ours(args, wl, rank, world, local_rank):
     obs_ring = eng.empty((nbuf, boards, 6, size, size), dtype=obs_dtype)
     rec = eng.new_records(boards)
     actions_log = torch.empty((W + K, boards), dtype=torch.int32, device=dev)
-    reward = eng.empty((boards,), dtype=torch.float32)
-    done = eng.empty((boards,))
+    reward_log = torch.empty((W + K, boards), dtype=torch.float32, device=dev)
+    done_log = torch.empty((W + K, boards), dtype=torch.uint8, device=dev)
 
     def plies(t0, count):
-        # ONE C call (gg_rollout) enqueues `count` launches of the fused kernel, one per ply, back to back
-        eng.rollout(rec, SEED, board0, t0, count, actions_log=actions_log[t0:], obs_ring=obs_ring, done=done,
-                    reward=reward, reward_mode=1, komi=0.0)
+        # ONE C call (gg_rollout): persistent kernel, args.plies_per_launch plies per launch, boards in registers
+        eng.rollout(rec, SEED, board0, t0, count, plies_per_launch=args.plies_per_launch, actions_log=actions_log[t0:],
+                    obs_ring=obs_ring, done_log=done_log[t0:], reward_log=reward_log[t0:], reward_mode=1, komi=0.0)
 
     def barrier():
         if world > 1:
@@ -286,8 +286,9 @@ def run_ours(args, wl, rank, world, local_rank):
         value = total_plies / t_max
         bytes_per_ply = algorithmic_bytes_per_ply(size, obs_elem)
         peak, peak_src = measured_peak_gbs()
-        launch_s = float(allr[0, 1]) / K
-        achieved = boards * bytes_per_ply / launch_s / 1e9
+        n_launches = -(-K // args.plies_per_launch)
+        launch_s = float(allr[0, 1]) / n_launches                      # average duration of one kernel launch
+        achieved = boards * bytes_per_ply * (K / float(n_launches)) / launch_s / 1e9
         line = {
             "metric": "env-steps/sec (batched random-legal rollout)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True,
@@ -299,16 +300,17 @@ def run_ours(args, wl, rank, world, local_rank):
                        "l2": "each step writes a %.0f MB observation (> L2) into one of %d rotating buffers; the "
                              "%.1f MB packed state is L2-resident by nature" % (dense_bytes / 1e6, nbuf,
                                                                                boards * eng.rec_bytes / 1e6),
+                       "plies_per_launch": args.plies_per_launch,
                        "parallelism": "dp%d (independent boards, no data-path collective)" % world},
             "e2e": {"value": e2e_plies / e2e_t, "unit": "env-steps/s",
                     "h2d_bytes_per_step": boards * 4 * world,
                     "d2h_bytes_per_step": (dense_bytes + boards * 5) * world, "steps": e2e_steps,
                     "api": "BatchedGoEnv.step(actions, auto_reset=True): pinned-host actions in; %s observation, reward, "
                            "done out to pinned host, stream-synchronised every step" % args.obs},
-            "gpu_launches": K,
+            "gpu_launches": -(-K // args.plies_per_launch),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gg::k_step<Geo<%d>, MODE_ROLLOUT>" % size,
+                         "traffic": None, "kernel": "gg::k_rollout<Geo<%d>> (%d plies per launch)" % (size, args.plies_per_launch),
                          "bytes_per_ply": bytes_per_ply, "peak_source": peak_src,
                          "launch_us": launch_s * 1e6},
         }
@@ -339,6 +341,8 @@ def main():
     ap.add_argument("--boards", type=int, default=None, help="boards per GPU (default: the workload's)")
     ap.add_argument("--obs", default="f32", choices=["f32", "u8"])
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--plies-per-launch", type=int, default=8,
+                    help="plies the persistent rollout kernel plays per launch (boards stay in registers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -55,7 +55,7 @@ def lib():
     L.gg_set_device.argtypes = [i32]
     L.gg_step.argtypes = [vp, vp, vp, vp, i64, i32, u32, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout_step.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, i32, f32, vp]
-    L.gg_rollout.argtypes = [vp, i64, i32, u64, u64, u64, i32, vp, vp, i32, i32, vp, vp, i32, f32, vp]
+    L.gg_rollout.argtypes = [vp, i64, i32, u64, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp, i32, f32, vp]
     L.gg_sample_legal.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp]
     L.gg_valid_moves.argtypes = [vp, i64, i32, i32, i32, vp, vp]
     L.gg_children.argtypes = [vp, i64, i32, u32, vp, vp, i32, vp, vp, vp]

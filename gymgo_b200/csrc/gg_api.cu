@@ -134,33 +134,34 @@ GG_API int gg_rollout_step(void* rec, int64_t batch, int n, uint64_t seed, uint6
 }
 
 GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
-               int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring, uint8_t* done_out, float* reward_out,
-               int reward_mode, float komi, void* stream) {
+               int plies_per_launch, int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring,
+               uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* stream) {
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
-    if (batch < 0 || steps < 0 || (batch > 0 && !rec)) return GG_EINVAL;
+    if (batch < 0 || steps < 0 || plies_per_launch < 1 || (batch > 0 && !rec)) return GG_EINVAL;
     if (obs_ring_buf && (!dense_dtype_ok(obs_dtype, false) || obs_ring < 1)) return GG_EINVAL;
     if (reward_mode < GG_REWARD_NONE || reward_mode > GG_REWARD_HEURISTIC) return GG_EINVAL;
     if (!aligned16(rec) || !aligned16(obs_ring_buf)) return GG_EALIGN;
     const size_t slot_bytes = size_t(batch) * 6u * size_t(n) * size_t(n) * (obs_dtype == GG_F32 ? 4u : 1u);
     if (obs_ring_buf && obs_ring > 1 && (slot_bytes & 15u)) return GG_EALIGN;
-    StepArgs a;
+    RolloutArgs a;
     memset(&a, 0, sizeof a);
-    a.rec_in = static_cast<const uint32_t*>(rec);
-    a.rec_out = static_cast<uint32_t*>(rec);
-    a.obs_dtype = obs_dtype;
-    a.done_out = done_out;
-    a.reward_out = reward_mode == GG_REWARD_NONE ? nullptr : reward_out;
-    a.reward_mode = reward_mode;
-    a.komi = komi;
-    a.slots = batch;
+    a.rec = static_cast<uint32_t*>(rec);
+    a.boards = batch;
     a.seed = seed;
     a.board0 = board0;
-    for (int p = 0; p < steps; ++p) {
-        a.t = t0 + uint64_t(p);
-        a.actions_out = actions_log ? actions_log + size_t(p) * size_t(batch) : nullptr;
-        a.obs = obs_ring_buf ? static_cast<char*>(obs_ring_buf) + size_t(a.t % uint64_t(obs_ring)) * slot_bytes : nullptr;
-        cudaError_t e = v->step(a, MODE_ROLLOUT, static_cast<cudaStream_t>(stream));
+    a.reward_mode = reward_mode;
+    a.komi = komi;
+    a.obs_ring = obs_ring_buf;
+    a.obs_dtype = obs_dtype;
+    a.ring = obs_ring_buf ? obs_ring : 1;
+    for (int p = 0; p < steps; p += plies_per_launch) {
+        a.t0 = t0 + uint64_t(p);
+        a.plies = steps - p < plies_per_launch ? steps - p : plies_per_launch;
+        a.actions_log = actions_log ? actions_log + size_t(p) * size_t(batch) : nullptr;
+        a.done_log = done_log ? done_log + size_t(p) * size_t(batch) : nullptr;
+        a.reward_log = (reward_log && reward_mode != GG_REWARD_NONE) ? reward_log + size_t(p) * size_t(batch) : nullptr;
+        cudaError_t e = v->rollout(a, static_cast<cudaStream_t>(stream));
         if (e != cudaSuccess) return finish(e);
     }
     return GG_OK;

@@ -207,6 +207,8 @@ struct Tile {
     static constexpr int BT = WPC * G::BPW;
     static constexpr int DENSE = 6 * G::NP;                      // elements per board
     static constexpr int STREAM_W32 = (BT * DENSE + 31) / 32 + 2;
+    // persistent rollout kernel: keep every CTA of the headline batches resident (9x9: 11.1 CTAs per SM)
+    static constexpr int ROLLOUT_MIN_BLOCKS = G::WB == 32 ? 12 : 8;
     static_assert(BT % 8 == 0, "tile must keep the dense output 16-byte aligned");
 };
 
@@ -231,12 +233,12 @@ __device__ __forceinline__ typename G::W compact_rows(typename G::W w) {
     return out;
 }
 template <class G>
-__device__ __forceinline__ void stream_put_board(uint32_t* s_bits, int slot_local, int j, typename G::W black,
+__device__ __forceinline__ void stream_put_board(uint32_t* s_bits, int board_bit0, int j, typename G::W black,
                                                  typename G::W white, typename G::W invd, uint32_t flags) {
     typedef typename G::W W;
     const int rows = G::rows_in_lane(j);
     if (rows == 0) return;
-    const int base = slot_local * Tile<G>::DENSE + j * G::RPL * G::N;
+    const int base = board_bit0 + j * G::RPL * G::N;
     const W ones = (W(1) << (rows * G::N)) - 1;       // rows*N < word bits by construction
     stream_put(s_bits, base + 0 * G::NP, compact_rows<G>(black));
     stream_put(s_bits, base + 1 * G::NP, compact_rows<G>(white));
@@ -246,33 +248,46 @@ __device__ __forceinline__ void stream_put_board(uint32_t* s_bits, int slot_loca
     stream_put(s_bits, base + 5 * G::NP, (flags & FLAG_DONE) ? ones : W(0));
 }
 
-// Expand `elems` stream bits to f32 / u8 at `dst` (16-byte aligned) with 128-bit stores.
-// f32: one stream nibble -> one float4 through a 16-entry shared-memory table (1 LDS.128 instead of 12 ALU ops).
-__device__ __forceinline__ void emit_f32(const uint32_t* s_bits, const float4* s_lut, int elems, float* dst, int tid,
-                                         int nthreads) {
-    const int nq = elems >> 2;
-    float4* dst4 = reinterpret_cast<float4*>(dst);
+// Expand stream bits [head, head+count) to f32 / u8.  Stream bit i belongs to element base[i]; `base` is
+// 16-byte aligned and the first `head` bits (< one vector) are padding, so that every full vector is one
+// aligned 128-bit store; only the first and last vector of a range can be partial (scalar stores).
+// f32: one stream nibble -> one float4 through a 16-entry shared-memory table (1 LDS.128, no ALU expansion).
+__device__ __forceinline__ void emit_f32(const uint32_t* s_bits, const float4* s_lut, int head, int count, float* base,
+                                         int tid, int nthreads) {
+    const int end = head + count;
+    const int nq = (end + 3) >> 2;
+    float4* base4 = reinterpret_cast<float4*>(base);
 #pragma unroll 4
     for (int q = tid; q < nq; q += nthreads) {
         const uint32_t nib = (s_bits[q >> 3] >> ((q & 7) << 2)) & 15u;
-        __stcs(dst4 + q, s_lut[nib]);
+        const int e = q << 2;
+        if (e >= head && e + 4 <= end) {
+            __stcs(base4 + q, s_lut[nib]);
+        } else {
+            for (int i = 0; i < 4; ++i)
+                if (e + i >= head && e + i < end) base[e + i] = ((nib >> i) & 1u) ? 1.0f : 0.0f;
+        }
     }
-    for (int e = (nq << 2) + tid; e < elems; e += nthreads)
-        dst[e] = ((s_bits[e >> 5] >> (e & 31)) & 1u) ? 1.0f : 0.0f;
 }
-__device__ __forceinline__ void emit_u8(const uint32_t* s_bits, int elems, uint8_t* dst, int tid, int nthreads) {
-    const int nq = elems >> 4;
-    uint4* dst4 = reinterpret_cast<uint4*>(dst);
+__device__ __forceinline__ void emit_u8(const uint32_t* s_bits, int head, int count, uint8_t* base, int tid, int nthreads) {
+    const int end = head + count;
+    const int nq = (end + 15) >> 4;
+    uint4* base4 = reinterpret_cast<uint4*>(base);
     for (int q = tid; q < nq; q += nthreads) {
-        const uint32_t h = s_bits[q >> 1] >> ((q & 1) << 4);
-        uint4 v;
-        v.x = ((h & 15u) * 0x00204081u) & 0x01010101u;          // 4 bits -> 4 bytes of 0/1
-        v.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-        v.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-        v.w = (((h >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-        __stcs(dst4 + q, v);
+        const uint32_t h = (s_bits[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
+        const int e = q << 4;
+        if (e >= head && e + 16 <= end) {
+            uint4 v;
+            v.x = ((h & 15u) * 0x00204081u) & 0x01010101u;          // 4 bits -> 4 bytes of 0/1
+            v.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            v.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+            v.w = (((h >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+            __stcs(base4 + q, v);
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (e + i >= head && e + i < end) base[e + i] = uint8_t((h >> i) & 1u);
+        }
     }
-    for (int e = (nq << 4) + tid; e < elems; e += nthreads) dst[e] = uint8_t((s_bits[e >> 5] >> (e & 31)) & 1u);
 }
 
 // =================================================================================================
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
         if (MODE == MODE_CHILDREN)
             for (int i = G::FLAGS_IDX + 1; i < G::REC_W32; ++i) my_rec[i] = 0;
     }
-    if (want_obs && holder) stream_put_board<G>(s_bits, slot_local, j, black, white, invd, flags);
+    if (want_obs && holder) stream_put_board<G>(s_bits, slot_local * T::DENSE, j, black, white, invd, flags);
     fence_proxy_async();            // generic-proxy writes to s_rec must be visible to the bulk store
     __syncthreads();
 
@@ -434,10 +449,151 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     if (want_obs) {
         const int elems = nb * T::DENSE;
         const long long ebase = tile_base * T::DENSE;
-        if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, elems, static_cast<float*>(a.obs) + ebase, tid, T::THREADS);
-        else emit_u8(s_bits, elems, static_cast<uint8_t*>(a.obs) + ebase, tid, T::THREADS);
+        if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, 0, elems, static_cast<float*>(a.obs) + ebase, tid, T::THREADS);
+        else emit_u8(s_bits, 0, elems, static_cast<uint8_t*>(a.obs) + ebase, tid, T::THREADS);
     }
     if (a.rec_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// =================================================================================================
+// Persistent rollout kernel: `plies` consecutive fused plies per launch.  The boards of a warp stay in
+// REGISTERS for the whole launch (records are staged in by one TMA bulk load per CTA and leave by one bulk
+// store at the end); every ply each warp resets its finished boards, samples, plays, and expands the dense
+// observation of ITS boards from a warp-private bit stream - no CTA barrier inside the ply loop, so warps
+// drift apart and the HBM-bound observation stores of some warps overlap the ALU-bound rules of others.
+// =================================================================================================
+struct RolloutArgs {
+    uint32_t* rec;              // [B] records, updated in place
+    long long boards;
+    unsigned long long seed, board0, t0;
+    int plies;
+    int32_t* actions_log;       // [plies, B] or NULL
+    uint8_t* done_log;          // [plies, B] or NULL
+    float* reward_log;          // [plies, B] or NULL
+    int reward_mode;
+    float komi;
+    void* obs_ring;             // [ring, B, 6, N, N] or NULL; ply t writes slot t % ring
+    int obs_dtype, ring;
+};
+
+template <class G>
+struct WarpStream {
+    static constexpr int DENSE = 6 * G::NP;
+    static constexpr int W32 = (G::BPW * DENSE + 15 + 31) / 32 + 2;     // + up to 15 padding bits in front
+};
+
+template <class G>
+__global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS) k_rollout(const RolloutArgs a) {
+    typedef typename G::W W;
+    typedef Tile<G> T;
+    typedef WarpStream<G> WS;
+    __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
+    __shared__ uint32_t s_bits_all[T::WPC][WS::W32];
+    __shared__ __align__(16) float4 s_lut[16];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile_base = (long long)blockIdx.x * T::BT;
+    const long long left = a.boards - tile_base;
+    const int nb = left < T::BT ? int(left) : T::BT;
+    const bool want_obs = a.obs_ring != nullptr;
+    uint32_t* s_bits = s_bits_all[warp];
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < 16) s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
+        bulk_g2s(s_rec, a.rec + tile_base * G::REC_W32, uint32_t(nb) * G::REC_BYTES, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const int slot_in_warp = lane / G::LPB;
+    const int slot_local = warp * G::BPW + slot_in_warp;
+    const bool real = slot_in_warp < G::BPW && slot_local < nb;
+    const long long slot = tile_base + slot_local;
+    DevOps<G> o;
+    o.init(lane, real);
+    const int j = o.j;
+    const bool holder = real && G::rows_in_lane(j) > 0;
+    uint32_t* my_rec = s_rec + slot_local * G::REC_W32;
+
+    W black = 0, white = 0, invd = 0;
+    uint32_t flags = 0;
+    if (holder) {
+        black = rec_word<G>(my_rec, 0, j);
+        white = rec_word<G>(my_rec, 1, j);
+        invd = rec_word<G>(my_rec, 2, j);
+    }
+    if (real) flags = my_rec[G::FLAGS_IDX];
+
+    // this warp's slice of the dense output: boards [wb0, wb0 + nbw)
+    const long long wb0 = tile_base + warp * G::BPW;
+    int nbw = nb - warp * G::BPW;
+    nbw = nbw < 0 ? 0 : (nbw > G::BPW ? G::BPW : nbw);
+    const long long e0 = wb0 * WS::DENSE;                          // first element inside an observation slot
+    const int align = a.obs_dtype == DT_F32 ? 4 : 16;              // elements per 16-byte vector
+    const int head = int(e0 % align);
+    const int count = nbw * WS::DENSE;
+    const long long slot_elems = a.boards * WS::DENSE;
+    const unsigned long long gb = a.board0 + (unsigned long long)slot;
+
+    for (int p = 0; p < a.plies; ++p) {
+        const unsigned long long t = a.t0 + (unsigned long long)p;
+        if (flags & FLAG_DONE) {                                   // auto-reset (gogame.init_state)
+            black = white = invd = 0;
+            flags = 0;
+        }
+        const uint32_t rnd = philox4x32_10(uint32_t(gb), uint32_t(gb >> 32), uint32_t(t), uint32_t(t >> 32),
+                                           uint32_t(a.seed), uint32_t(a.seed >> 32));
+        const int action = Algo<DevOps<G>>::sample_action(o, G(), invd, rnd);
+        Algo<DevOps<G>>::step(o, G(), black, white, invd, flags, action, 0u);
+
+        const bool over = (flags & FLAG_DONE) != 0;
+        const long long log_at = (long long)p * a.boards + slot;
+        if (real && j == 0) {
+            if (a.actions_log) a.actions_log[log_at] = action;
+            if (a.done_log) a.done_log[log_at] = over ? 1 : 0;
+        }
+        if (a.reward_log) {
+            const bool need_areas = a.reward_mode == 2 || __any_sync(0xffffffffu, over);
+            float r = 0.f;
+            if (need_areas) {
+                int ba, wa;
+                Algo<DevOps<G>>::areas(o, black, white, ba, wa);
+                const float diff = float(ba - wa) - a.komi;
+                if (a.reward_mode == 1) r = over ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+                else r = over ? (diff > 0.f ? float(G::NP) : -float(G::NP)) : diff;
+            }
+            if (real && j == 0) a.reward_log[log_at] = r;
+        }
+        if (want_obs) {
+            for (int i = lane; i < WS::W32; i += 32) s_bits[i] = 0;
+            __syncwarp();
+            if (holder) stream_put_board<G>(s_bits, head + slot_in_warp * WS::DENSE, j, black, white, invd, flags);
+            __syncwarp();
+            const long long at = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0 - head;
+            if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane, 32);
+            else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
+            __syncwarp();
+        }
+    }
+
+    if (holder) {
+        rec_word_store<G>(my_rec, 0, j, black);
+        rec_word_store<G>(my_rec, 1, j, white);
+        rec_word_store<G>(my_rec, 2, j, invd);
+    }
+    if (real && j == 0) my_rec[G::FLAGS_IDX] = flags;
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(a.rec + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
+        bulk_commit_wait_all();
+    }
 }
 
 // ------------------------------------------------------------------ warp-layout helper kernels
@@ -586,6 +742,7 @@ __global__ void k_canonical(const uint32_t* in, uint32_t* out, long long batch) 
 struct SizeVTable {
     int n, rec_bytes, lpb, rpl, wordbits, bpw, tile_boards, tile_threads;
     cudaError_t (*step)(const StepArgs&, int mode, cudaStream_t);
+    cudaError_t (*rollout)(const RolloutArgs&, cudaStream_t);
     cudaError_t (*areas)(const uint32_t*, long long, int32_t*, cudaStream_t);
     cudaError_t (*sample)(const uint32_t*, long long, unsigned long long, unsigned long long, unsigned long long, int32_t*,
                           cudaStream_t);
@@ -606,6 +763,11 @@ struct Launch {
         if (mode == MODE_STEP) k_step<G, MODE_STEP><<<grid, Tile<G>::THREADS, 0, s>>>(a);
         else if (mode == MODE_ROLLOUT) k_step<G, MODE_ROLLOUT><<<grid, Tile<G>::THREADS, 0, s>>>(a);
         else k_step<G, MODE_CHILDREN><<<grid, Tile<G>::THREADS, 0, s>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t rollout(const RolloutArgs& a, cudaStream_t s) {
+        if (a.boards <= 0 || a.plies <= 0) return cudaSuccess;
+        k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t areas(const uint32_t* rec, long long batch, int32_t* out, cudaStream_t s) {
@@ -656,7 +818,7 @@ struct Launch {
     }
     static constexpr SizeVTable table() {
         return SizeVTable{G::N, G::REC_BYTES, G::LPB, G::RPL, G::WB, G::BPW, Tile<G>::BT, Tile<G>::THREADS,
-                          &step, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical};
+                          &step, &rollout, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical};
     }
 };
 

@@ -138,16 +138,17 @@ class GoEngine(object):
                                              _ptr(actions), _ptr(obs), _TORCH2GG[obs.dtype] if obs is not None else 0,
                                              _ptr(done), _ptr(areas), _ptr(reward), int(reward_mode), float(komi), s))
 
-    def rollout(self, rec, seed, board0, t0, steps, actions_log=None, obs_ring=None, done=None, reward=None,
-                reward_mode=0, komi=0.0):
-        """`steps` fused rollout plies enqueued by ONE C call (gg_rollout).  obs_ring: [R,B,6,N,N] ring of
-        observation slots (ply t writes slot t % R); actions_log: int32 [steps,B]."""
+    def rollout(self, rec, seed, board0, t0, steps, plies_per_launch=8, actions_log=None, obs_ring=None,
+                done_log=None, reward_log=None, reward_mode=0, komi=0.0):
+        """`steps` fused rollout plies by the persistent kernel (gg_rollout), `plies_per_launch` plies per launch.
+        obs_ring: [R,B,6,N,N] ring of observation slots (ply t writes slot t % R); actions_log int32 [steps,B],
+        done_log uint8 [steps,B], reward_log float32 [steps,B] - all optional, preallocated."""
         s = self._enter()
         ring = 0 if obs_ring is None else int(obs_ring.shape[0])
         _cabi.check(self.lib.gg_rollout(_ptr(rec), rec.shape[0], self.size, int(seed), int(board0), int(t0), int(steps),
-                                        _ptr(actions_log), _ptr(obs_ring),
-                                        _TORCH2GG[obs_ring.dtype] if obs_ring is not None else 0, ring, _ptr(done),
-                                        _ptr(reward), int(reward_mode), float(komi), s))
+                                        int(plies_per_launch), _ptr(actions_log), _ptr(obs_ring),
+                                        _TORCH2GG[obs_ring.dtype] if obs_ring is not None else 0, ring, _ptr(done_log),
+                                        _ptr(reward_log), int(reward_mode), float(komi), s))
 
     def sample_legal(self, rec, seed, board0, t):
         self._check_rec(rec)

@@ -122,13 +122,17 @@ GG_API int gg_rollout_step(void *rec, int64_t batch, int n, uint64_t seed, uint6
                            int32_t *actions_out, void *obs_out, int obs_dtype, uint8_t *done_out, int32_t *areas_out,
                            float *reward_out, int reward_mode, float komi, void *stream);
 
-/* `steps` consecutive gg_rollout_step plies (t = t0 .. t0+steps-1) enqueued back to back from C, so a Python
- * caller pays one call instead of one per ply.  Ply p writes its observation to slot (t0+p) % obs_ring of
- * obs_ring_buf ([obs_ring, B, 6, N, N], may be NULL) and its actions to actions_log[p] ([steps, B], may be
- * NULL); done_out / reward_out (may be NULL) hold the values of the last ply. */
+/* Device-side rollout driver: `steps` consecutive fused plies (t = t0 .. t0+steps-1, same semantics and same
+ * trajectories as gg_rollout_step) executed by a PERSISTENT kernel that keeps every board in registers for
+ * `plies_per_launch` plies per launch (1 = one launch per ply).  Per ply p it writes
+ *   actions_log[p]  int32 [steps, B]  (may be NULL)      done_log[p]    uint8   [steps, B] (may be NULL)
+ *   reward_log[p]   float32 [steps, B] (may be NULL; GoEnv.reward for reward_mode / komi)
+ *   the observation of ply t into slot t % obs_ring of obs_ring_buf ([obs_ring, B, 6, N, N], may be NULL);
+ * warps run ahead of each other inside a launch, so a caller that wants every observation of a launch
+ * passes obs_ring >= plies_per_launch.  The packed records are read once and written once per launch. */
 GG_API int gg_rollout(void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
-                      int32_t *actions_log, void *obs_ring_buf, int obs_dtype, int obs_ring, uint8_t *done_out,
-                      float *reward_out, int reward_mode, float komi, void *stream);
+                      int plies_per_launch, int32_t *actions_log, void *obs_ring_buf, int obs_dtype, int obs_ring,
+                      uint8_t *done_log, float *reward_log, int reward_mode, float komi, void *stream);
 
 /* The sampler alone (no reset, no step): actions_out[b] = uniformly random valid action of board b.
  * Replaces: GoEnv.uniform_random_action / gogame.random_action (go_env.py:78-81, gogame.py:395-404). */

@@ -141,6 +141,42 @@ def test_rollout_vs_oracle_replay(eng, n, boards, steps):
         assert finished > 0
 
 
+@pytest.mark.parametrize("n,boards", ((9, 1003), (19, 149), (7, 333), (5, 77), (17, 41), (13, 64)))
+@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8))
+def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
+    """gg_rollout (boards resident in registers for several plies, per-warp observation emission incl. ragged
+    tiles and unaligned warp slices) reproduces the ply-by-ply kernel bit for bit: records, observations of every
+    ply, actions, done flags, rewards."""
+    from gymgo_b200 import _cabi
+    e = eng(n)
+    steps, ppl, seed, board0, t0 = 37, 5, 99, 1234, 17
+    warm = e.new_records(boards)
+    for t in range(t0):
+        e.rollout_step(warm, seed, board0, t)
+    a = warm.clone()
+    b = warm.clone()
+    ring = e.empty((steps + 1, boards, 6, n, n), dtype=dtype)
+    ring.fill_(7)
+    acts = torch.full((steps, boards), -5, dtype=torch.int32, device="cuda")
+    dones = torch.full((steps, boards), 9, dtype=torch.uint8, device="cuda")
+    rews = torch.full((steps, boards), 9.0, dtype=torch.float32, device="cuda")
+    e.rollout(a, seed, board0, t0, steps, plies_per_launch=ppl, actions_log=acts, obs_ring=ring, done_log=dones,
+              reward_log=rews, reward_mode=_cabi.GG_REWARD_HEURISTIC, komi=0.5)
+    obs1 = e.empty((boards, 6, n, n), dtype=dtype)
+    a1 = e.empty((boards,), dtype=torch.int32)
+    d1 = e.empty((boards,))
+    r1 = e.empty((boards,), dtype=torch.float32)
+    for p in range(steps):
+        t = t0 + p
+        e.rollout_step(b, seed, board0, t, actions=a1, obs=obs1, done=d1, reward=r1,
+                       reward_mode=_cabi.GG_REWARD_HEURISTIC, komi=0.5)
+        assert torch.equal(ring[t % (steps + 1)], obs1), (p, "obs")
+        assert torch.equal(acts[p], a1) and torch.equal(dones[p], d1) and torch.equal(rews[p], r1), p
+    assert torch.equal(a, b)
+    untouched = [s for s in range(steps + 1) if s not in {(t0 + p) % (steps + 1) for p in range(steps)}]
+    assert all(bool((ring[s] == 7).all()) for s in untouched)
+
+
 @pytest.mark.parametrize("n", golden_io.CHILDREN_SIZES)
 def test_children_golden(eng, n):
     e = eng(n)

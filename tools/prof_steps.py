@@ -30,9 +30,13 @@ for size, boards in ((9, 65536), (19, 16384)):
     chunks = []
     t = 0
     for _ in range(16):
-        us = timed(lambda: eng.rollout(rec, 0, 0, t, 50, obs_ring=ring, done=done, reward=rew, reward_mode=1))
+        us = timed(lambda: eng.rollout(rec, 0, 0, t, 50, obs_ring=ring))
         t += 50
         chunks.append(round(us / 50, 2))
+    ppl = {}
+    for k in (1, 2, 4, 8, 16, 50):
+        ppl[k] = round(timed(lambda: eng.rollout(rec, 0, 0, t, 50, plies_per_launch=k, obs_ring=ring)) / 50, 2)
+        t += 50
     noobs = timed(lambda: eng.rollout(rec, 0, 0, t, 50, obs_ring=None)) / 50
     t += 50
     u8ring = eng.empty((3, boards, 6, size, size), dtype=torch.uint8)
@@ -50,6 +54,6 @@ for size, boards in ((9, 65536), (19, 16384)):
         eng.rollout_step(small, 0, 0, k)
     torch.cuda.synchronize()
     host = (time.time() - t0) / 2000 * 1e6
-    out["%dx%d" % (size, size)] = dict(us_per_ply_by_50=chunks, no_obs_us=round(noobs, 2), u8_us=round(u8, 2),
+    out["%dx%d" % (size, size)] = dict(us_per_ply_by_50=chunks, us_per_ply_by_plies_per_launch=ppl, no_obs_us=round(noobs, 2), u8_us=round(u8, 2),
                                        python_loop_us=round(py, 2), host_call_us_tiny_batch=round(host, 2))
 print(json.dumps(out))
