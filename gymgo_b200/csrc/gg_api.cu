@@ -142,8 +142,6 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
     if (obs_ring_buf && (!dense_dtype_ok(obs_dtype, false) || obs_ring < 1)) return GG_EINVAL;
     if (reward_mode < GG_REWARD_NONE || reward_mode > GG_REWARD_HEURISTIC) return GG_EINVAL;
     if (!aligned16(rec) || !aligned16(obs_ring_buf)) return GG_EALIGN;
-    const size_t slot_bytes = size_t(batch) * 6u * size_t(n) * size_t(n) * (obs_dtype == GG_F32 ? 4u : 1u);
-    if (obs_ring_buf && obs_ring > 1 && (slot_bytes & 15u)) return GG_EALIGN;
     RolloutArgs a;
     memset(&a, 0, sizeof a);
     a.rec = static_cast<uint32_t*>(rec);

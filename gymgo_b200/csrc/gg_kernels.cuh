@@ -535,8 +535,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     int nbw = nb - warp * G::BPW;
     nbw = nbw < 0 ? 0 : (nbw > G::BPW ? G::BPW : nbw);
     const long long e0 = wb0 * WS::DENSE;                          // first element inside an observation slot
-    const int align = a.obs_dtype == DT_F32 ? 4 : 16;              // elements per 16-byte vector
-    const int head = int(e0 % align);
+    const int align_mask = a.obs_dtype == DT_F32 ? 3 : 15;         // elements per 16-byte vector, minus 1
     const int count = nbw * WS::DENSE;
     const long long slot_elems = a.boards * WS::DENSE;
     const unsigned long long gb = a.board0 + (unsigned long long)slot;
@@ -571,11 +570,14 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
             if (real && j == 0) a.reward_log[log_at] = r;
         }
         if (want_obs) {
+            // absolute element index of this warp's first value; the slot stride need not be a multiple of 16 bytes
+            const long long abs0 = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0;
+            const int head = int(abs0 & align_mask);
+            const long long at = abs0 - head;
             for (int i = lane; i < WS::W32; i += 32) s_bits[i] = 0;
             __syncwarp();
             if (holder) stream_put_board<G>(s_bits, head + slot_in_warp * WS::DENSE, j, black, white, invd, flags);
             __syncwarp();
-            const long long at = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0 - head;
             if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane, 32);
             else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
             __syncwarp();
