@@ -273,13 +273,8 @@ def run_ours(args, wl, rank, world, local_rank):
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
 
     # ---------------- gather (plies, seconds) of every rank: the only collective of the job
-    mine = torch.tensor([float(boards) * K, secs, float(boards) * e2e_steps, e2e_secs], dtype=torch.float64, device=dev)
-    if world > 1:
-        allr = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        allr = torch.stack(allr).cpu()
-    else:
-        allr = mine.cpu().reshape(1, 4)
+    from gymgo_b200 import sharding
+    allr = sharding.gather_counters([float(boards) * K, secs, float(boards) * e2e_steps, e2e_secs], device=dev)
     if rank == 0:
         total_plies, t_max = float(allr[:, 0].sum()), float(allr[:, 1].max())
         e2e_plies, e2e_t = float(allr[:, 2].sum()), float(allr[:, 3].max())
