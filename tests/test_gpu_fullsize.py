@@ -1,0 +1,82 @@
+"""GPU tests at BASELINE.json's full sizes.  The oracle cannot replay 65,536 boards ply by ply in seconds, so
+these use (a) the host simulator of the device algorithm on the whole batch (C++, bit-identical records and
+actions expected), (b) size-independent invariants, (c) the C oracle on a strided sample of transitions."""
+import numpy as np
+import pytest
+import torch
+
+import hostsim
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+def invariants(dense):
+    black, white, invd = dense[:, 0], dense[:, 1], dense[:, 3]
+    assert not (black & white).any()                                   # a point holds one stone at most
+    assert ((black | white) <= invd).all()                             # occupied points are invalid
+    for ch in (2, 4, 5):                                               # whole-plane facts are constant planes
+        p = dense[:, ch].reshape(len(dense), -1)
+        assert (p.min(axis=1) == p.max(axis=1)).all()
+
+
+@pytest.mark.parametrize("n,boards,plies,ppl", ((9, 65536, 48, 8), (19, 16384, 40, 5)))
+def test_full_batch_rollout_equals_host_simulation(n, boards, plies, ppl):
+    from gymgo_b200.engine import GoEngine
+    e = GoEngine(n, "cuda:0")
+    rec = e.new_records(boards)
+    acts = torch.empty((plies, boards), dtype=torch.int32, device="cuda")
+    ring = e.empty((2, boards, 6, n, n), dtype=torch.uint8)
+    e.rollout(rec, 11, 5_000_000_000, 0, plies, plies_per_launch=ppl, actions_log=acts, obs_ring=ring)
+    sim = hostsim.pack(np.zeros((boards, 6, n, n), dtype=np.uint8))
+    sim_acts = np.stack([hostsim.rollout_step(sim, n, 11, 5_000_000_000, t) for t in range(plies)])
+    assert np.array_equal(acts.cpu().numpy(), sim_acts)
+    assert np.array_equal(rec.cpu().numpy().view(np.uint32), sim)
+    last = ring[(plies - 1) % 2].cpu().numpy()
+    assert np.array_equal(last, hostsim.unpack(sim, n))
+    invariants(last)
+    # oracle on a strided sample of the final transition
+    idx = np.arange(0, boards, 97)
+    prev = e.new_records(boards)
+    e.rollout(prev, 11, 5_000_000_000, 0, plies - 1, plies_per_launch=ppl)
+    before = e.unpack(prev, dtype=torch.uint8).cpu().numpy()[idx]
+    before[before[:, 5, 0, 0] == 1] = 0                                # auto-reset precedes the ply
+    want, status = co.batch_next_states(before, sim_acts[-1][idx])
+    assert not status.any() and np.array_equal(want, last[idx])
+
+
+def test_children_full_config():
+    """configs[3]: 9x9 children() of 4,096 parents after 40 random plies; every slot against per-action gg_step,
+    a sample against the C oracle."""
+    from gymgo_b200.engine import GoEngine
+    e = GoEngine(9, "cuda:0")
+    parents = e.new_records(4096)
+    e.rollout(parents, 0, 0, 0, 40, plies_per_launch=8)
+    e.reset(parents, e.flags(parents) & 4 != 0)                        # drop the few finished games
+    res = e.children(parents, obs_dtype=torch.uint8, want_rec=True)
+    assert not res["status"].any()
+    valid = res["valid"].cpu().numpy()
+    dense_parents = e.unpack(parents, dtype=torch.uint8).cpu().numpy()
+    assert np.array_equal(valid[:, :81], 1 - dense_parents[:, 3].reshape(4096, 81)) and (valid[:, 81] == 1).all()
+    for a in (0, 17, 40, 80, 81):                                      # whole columns of the expansion vs gg_step
+        acts = torch.full((4096,), a, dtype=torch.int32, device="cuda")
+        step = e.step(parents, acts, obs_dtype=torch.uint8)
+        ok = step["status"].cpu().numpy() == 0
+        assert np.array_equal(ok, valid[:, a] == 1)
+        assert np.array_equal(res["obs"][:, a].cpu().numpy()[ok], step["obs"].cpu().numpy()[ok])
+        assert not res["obs"][:, a].cpu().numpy()[~ok].any()           # padded zeros
+        assert torch.equal(res["rec"][:, a][torch.from_numpy(ok).cuda()], step["rec"][torch.from_numpy(ok).cuda()])
+    for i in range(0, 4096, 311):
+        kids, v, bad = co.children(dense_parents[i])
+        assert not bad and np.array_equal(res["obs"][i].cpu().numpy(), kids)
+
+
+def test_shard_invariance_full_size():
+    """two half batches with board offsets reproduce the whole batch (what the multi-GPU run relies on)"""
+    from gymgo_b200.engine import GoEngine
+    e = GoEngine(9, "cuda:0")
+    whole, lo, hi = e.new_records(8192), e.new_records(4096), e.new_records(4096)
+    e.rollout(whole, 3, 0, 0, 64, plies_per_launch=8)
+    e.rollout(lo, 3, 0, 0, 64, plies_per_launch=4)
+    e.rollout(hi, 3, 4096, 0, 64, plies_per_launch=16)
+    assert torch.equal(whole[:4096], lo) and torch.equal(whole[4096:], hi)

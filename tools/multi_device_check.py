@@ -1,7 +1,12 @@
 """Developer check: the library (own static CUDA runtime) works on a non-zero device ordinal and on two
 devices from one process."""
+import os
+import sys
+
 import numpy as np
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from gymgo_b200.engine import GoEngine
 from oracle import c_oracle as co
