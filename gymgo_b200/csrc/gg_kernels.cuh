@@ -252,21 +252,26 @@ __device__ __forceinline__ void stream_put_board(uint32_t* s_bits, int board_bit
 // 16-byte aligned and the first `head` bits (< one vector) are padding, so that every full vector is one
 // aligned 128-bit store; only the first and last vector of a range can be partial (scalar stores).
 // f32: one stream nibble -> one float4 through a 16-entry shared-memory table (1 LDS.128, no ALU expansion).
+// With a stride of NT = 32*k threads a thread always reads the same nibble position of successive words, so
+// the inner loop is: LDS word, shift (loop-invariant amount), mask, LDS.128 table, STG.128, two pointer bumps.
+template <int NT>
 __device__ __forceinline__ void emit_f32(const uint32_t* s_bits, const float4* s_lut, int head, int count, float* base,
-                                         int tid, int nthreads) {
+                                         int tid) {
+    static_assert(NT % 32 == 0, "stride must keep the nibble position fixed per thread");
     const int end = head + count;
-    const int nq = (end + 3) >> 2;
+    const int q_lo = (head + 3) >> 2, q_hi = end >> 2;             // full vectors are [q_lo, q_hi)
     float4* base4 = reinterpret_cast<float4*>(base);
+    const int sh = (tid & 7) << 2;
+    int q = tid;
+    if (q < q_lo) q += NT;                                          // q_lo is 0 or 1
+    const uint32_t* w = s_bits + (q >> 3);
+    float4* g = base4 + q;
 #pragma unroll 4
-    for (int q = tid; q < nq; q += nthreads) {
-        const uint32_t nib = (s_bits[q >> 3] >> ((q & 7) << 2)) & 15u;
-        const int e = q << 2;
-        if (e >= head && e + 4 <= end) {
-            __stcs(base4 + q, s_lut[nib]);
-        } else {
-            for (int i = 0; i < 4; ++i)
-                if (e + i >= head && e + i < end) base[e + i] = ((nib >> i) & 1u) ? 1.0f : 0.0f;
-        }
+    for (; q < q_hi; q += NT, w += NT / 8, g += NT) __stcs(g, s_lut[(*w >> sh) & 15u]);
+    if (tid < 8) {                                                  // the (at most two) partial vectors
+        const int e = tid < 4 ? tid : (q_hi << 2) + tid - 4;        // elements 0..3 and the last vector's
+        if (e >= head && e < end && (e < (q_lo << 2) || e >= (q_hi << 2)))
+            base[e] = ((s_bits[e >> 5] >> (e & 31)) & 1u) ? 1.0f : 0.0f;
     }
 }
 __device__ __forceinline__ void emit_u8(const uint32_t* s_bits, int head, int count, uint8_t* base, int tid, int nthreads) {
@@ -449,7 +454,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     if (want_obs) {
         const int elems = nb * T::DENSE;
         const long long ebase = tile_base * T::DENSE;
-        if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, 0, elems, static_cast<float*>(a.obs) + ebase, tid, T::THREADS);
+        if (a.obs_dtype == DT_F32) emit_f32<T::THREADS>(s_bits, s_lut, 0, elems, static_cast<float*>(a.obs) + ebase, tid);
         else emit_u8(s_bits, 0, elems, static_cast<uint8_t*>(a.obs) + ebase, tid, T::THREADS);
     }
     if (a.rec_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
             __syncwarp();
             if (holder) stream_put_board<G>(s_bits, head + slot_in_warp * WS::DENSE, j, black, white, invd, flags);
             __syncwarp();
-            if (a.obs_dtype == DT_F32) emit_f32(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane, 32);
+            if (a.obs_dtype == DT_F32) emit_f32<32>(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane);
             else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
             __syncwarp();
         }
