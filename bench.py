@@ -41,6 +41,15 @@ def algorithmic_bytes_per_ply(n, obs_bytes_per_elem):
     return 2 * r + 4 + 6 * n * n * obs_bytes_per_elem
 
 
+def profiled_traffic(workload, obs, plies_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this configuration (or None)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["%s/%s/%d" % (workload, obs, plies_per_launch)]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -305,7 +314,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "gpu_launches": -(-K // args.plies_per_launch),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gg::k_rollout<Geo<%d>> (%d plies per launch)" % (size, args.plies_per_launch),
+                         "traffic": profiled_traffic(args.workload, args.obs, args.plies_per_launch),
+                         "algorithmic_bytes_per_launch": boards * bytes_per_ply * args.plies_per_launch, "kernel": "gg::k_rollout<Geo<%d>> (%d plies per launch)" % (size, args.plies_per_launch),
                          "bytes_per_ply": bytes_per_ply, "peak_source": peak_src,
                          "launch_us": launch_s * 1e6},
         }
