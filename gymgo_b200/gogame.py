@@ -253,22 +253,28 @@ def num_liberties(state):
     return np.count_nonzero(b), np.count_nonzero(w)
 
 
+def _rot90(image, k):
+    return torch.rot90(image, k, dims=(-2, -1)) if _is_torch(image) else np.rot90(image, k, axes=(-2, -1))
+
+
+def _flip(image):
+    return torch.flip(image, dims=(-1,)) if _is_torch(image) else np.flip(image, -1)
+
+
 def random_symmetry(image):
-    """gogame.py:340-355: one of the 8 dihedral transforms of the last two axes."""
-    k = np.random.randint(0, 4)
-    out = np.rot90(image, k, axes=(-2, -1))
-    if np.random.randint(0, 2):
-        out = np.flip(out, -1)
-    return out
+    """gogame.py:340-355: one of the 8 dihedral transforms of the last two axes (numpy or torch, any leading
+    batch/channel axes; torch tensors stay on their device)."""
+    out = _rot90(image, int(np.random.randint(0, 4)))
+    return _flip(out) if np.random.randint(0, 2) else out
 
 
 def all_symmetries(image):
-    """gogame.py:358-382: the 8 dihedral transforms."""
+    """gogame.py:358-382: the 8 dihedral transforms (numpy or torch)."""
     out = []
     for flip in (False, True):
-        base = np.flip(image, -1) if flip else image
+        base = _flip(image) if flip else image
         for k in range(4):
-            out.append(np.rot90(base, k, axes=(-2, -1)))
+            out.append(_rot90(base, k))
     return out
 
 

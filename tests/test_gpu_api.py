@@ -129,3 +129,57 @@ def test_batched_env_random_step_is_shard_invariant():
         oh, _, _, ah = hi.random_step()
         assert torch.equal(ow[:48], ol) and torch.equal(ow[48:], oh)
         assert torch.equal(aw[:48], al) and torch.equal(aw[48:], ah)
+
+
+def test_state_utils_and_symmetries():
+    from gym_go import gogame, state_utils
+    from test_device_algo_hostsim import random_soup
+    st = random_soup(7, 40, np.random.RandomState(3)).astype(np.float64)
+    for i in range(len(st)):
+        player = int(i % 2)
+        ko = None if i % 3 else (i % 7, (3 * i) % 7)
+        assert np.array_equal(state_utils.compute_invalid_moves(st[i], player, ko), og.invalid_mask(st[i], player, ko))
+    s = st[0].copy()
+    state_utils.set_turn(s)
+    assert (s[2] == 1 - st[0][2]).all()
+    nb, sur = state_utils.adj_data(st[1], (0, 0), 0)
+    assert len(nb) == 2
+    img = np.arange(2 * 6 * 5 * 5).reshape(2, 6, 5, 5)
+    sym_np = gogame.all_symmetries(img)
+    sym_t = gogame.all_symmetries(torch.from_numpy(img).cuda())
+    assert len(sym_np) == 8 and all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(sym_np, sym_t))
+    assert len({a.tobytes() for a in sym_np}) == 8
+
+
+def test_cuda_graph_capture_of_step_calls():
+    """the C ABI only enqueues kernels on the caller's stream, so a sequence of plies can be captured into a CUDA
+    graph and replayed"""
+    from gymgo_b200.engine import GoEngine
+    e = GoEngine(9, "cuda:0")
+    start = e.new_records(2048)
+    e.rollout(start, 1, 0, 0, 30)
+    acts = [e.empty((2048,), dtype=torch.int32) for _ in range(4)]
+    obs = e.empty((2048, 6, 9, 9), dtype=torch.float32)
+    rec = start.clone()
+
+    def four_plies():
+        for k in range(4):
+            e.lib.gg_sample_legal(rec.data_ptr(), 2048, 9, 5, 0, k, acts[k].data_ptr(), torch.cuda.current_stream().cuda_stream)
+            e.lib.gg_step(rec.data_ptr(), acts[k].data_ptr(), rec.data_ptr(), None, 2048, 9, 0, obs.data_ptr(), 1, None,
+                          None, None, 0, 0.0, torch.cuda.current_stream().cuda_stream)
+
+    e._enter()
+    four_plies()
+    torch.cuda.synchronize()
+    want_rec, want_obs = rec.clone(), obs.clone()
+    rec.copy_(start)
+    obs.zero_()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            four_plies()
+    rec.copy_(start)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(rec, want_rec) and torch.equal(obs, want_obs)
