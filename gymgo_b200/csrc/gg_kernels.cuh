@@ -432,7 +432,9 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
         a.reward_out[slot] = 0.f;
     }
 
-    // new record -> shared tile (padding words: kept from the input for STEP/ROLLOUT, zeroed for CHILDREN)
+    // new record -> shared tile (padding words: kept from the input for STEP/ROLLOUT, zeroed for CHILDREN).
+    // Every lane of a board read the flags word above; order those reads before lane 0 overwrites it.
+    __syncwarp();
     if (holder) {
         rec_word_store<G>(my_rec, 0, j, black);
         rec_word_store<G>(my_rec, 1, j, white);
@@ -589,6 +591,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
         }
     }
 
+    __syncwarp();                                                  // flags word: reads (all lanes) before the write
     if (holder) {
         rec_word_store<G>(my_rec, 0, j, black);
         rec_word_store<G>(my_rec, 1, j, white);
