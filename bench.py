@@ -250,6 +250,19 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     final_rec = rec.clone()
 
+    # ---------------- transparency: the same plies with ONE launch per ply (no register residency across plies)
+    scratch = rec.clone()
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n1 = min(K, 100)
+    eng.rollout(scratch, SEED, board0, W + K, 8, plies_per_launch=1, obs_ring=obs_ring)
+    torch.cuda.synchronize()
+    ev4.record()
+    eng.rollout(scratch, SEED, board0, W + K + 8, n1, plies_per_launch=1, obs_ring=obs_ring, done_log=done_log,
+                reward_log=reward_log, actions_log=actions_log, reward_mode=1, komi=0.0)
+    ev5.record()
+    torch.cuda.synchronize()
+    one_ply_secs = ev4.elapsed_time(ev5) / 1e3
+
     # ---------------- e2e: the public BatchedGoEnv.step with HOST buffers, copies inside the timed region
     actions_host = torch.empty((W + K, boards), dtype=torch.int32, pin_memory=True)
     actions_host.copy_(actions_log)
@@ -312,6 +325,9 @@ def run_ours(args, wl, rank, world, local_rank):
                     "api": "BatchedGoEnv.step(actions, auto_reset=True): pinned-host actions in; %s observation, reward, "
                            "done out to pinned host, stream-synchronised every step" % args.obs},
             "gpu_launches": -(-K // args.plies_per_launch),
+            "one_launch_per_ply": {"value": boards * n1 * world / one_ply_secs, "ms_per_step": 1e3 * one_ply_secs / n1,
+                                   "note": "rank-0 timing of the same kernel with plies_per_launch=1 (records reloaded "
+                                           "and stored every ply)"},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(args.workload, args.obs, args.plies_per_launch),
