@@ -258,7 +258,7 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.synchronize()
     ev4.record()
     eng.rollout(scratch, SEED, board0, W + K + 8, n1, plies_per_launch=1, obs_ring=obs_ring, done_log=done_log,
-                reward_log=reward_log, actions_log=actions_log, reward_mode=1, komi=0.0)
+                reward_log=reward_log, reward_mode=1, komi=0.0)     # (actions_log is kept intact for the e2e replay)
     ev5.record()
     torch.cuda.synchronize()
     one_ply_secs = ev4.elapsed_time(ev5) / 1e3
