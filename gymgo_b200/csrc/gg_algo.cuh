@@ -29,6 +29,11 @@
 #define GG_HD inline
 #endif
 
+// developer hook: the host simulator can tag which flood is running (tools/algo_stats.py); a no-op on the device
+#ifndef GG_STAT_TAG
+#define GG_STAT_TAG(k)
+#endif
+
 namespace gg {
 
 enum : uint32_t { FLAG_TURN = 1u, FLAG_PASS = 2u, FLAG_DONE = 4u };
@@ -226,7 +231,9 @@ struct Algo {
             const P open = o.andnot(empty, pockets);   // liberties that have an empty neighbour
             const P two = (ee & ew) | (es & en) | ((ee | ew) & (es | en));   // touches >= 2 empty points
             const P healthy = nbrs(o, open) | two;
+            GG_STAT_TAG(2)
             const P big_nxt = flood(o, nxt & healthy, nxt);                // groups with >= 2 liberties (sufficient)
+            GG_STAT_TAG(3)
             const P big_oth = flood(o, oth & healthy, oth);
             bad = o.andnot(bad, nbrs(o, big_nxt));     // own group with >= 2 liberties: safe
             const P rest_nxt = o.andnot(nxt, big_nxt);
@@ -242,6 +249,7 @@ struct Algo {
                 while (o.any(todo)) {
                     const P s = o.lowest(todo);
                     const bool mine = o.any_board(s & nxt);
+                    GG_STAT_TAG(4)
                     const P grp = flood(o, s, o.pick(mine, rest_nxt, rest_oth), o.pick(mine, rrev_nxt, rrev_oth));
                     const P libs = nbrs(o, grp) & empty;
                     const int nl = o.count2(libs);
@@ -284,7 +292,9 @@ struct Algo {
         const P seeds = nb & opp;
         if (o.any(seeds)) {
             const P empty = o.andnot(o.full(), own | opp);
+            GG_STAT_TAG(0)
             const P grp = flood(o, seeds, opp);                    // every opponent group touching the move
+            GG_STAT_TAG(1)
             const P alive = flood(o, grp & nbrs(o, empty), grp);   // ... that still has a liberty
             const P dead = o.andnot(grp, alive);
             opp = o.andnot(opp, dead);

@@ -8,6 +8,9 @@
 #include <stdint.h>
 #include <string.h>
 
+static int g_stat_tag = 0;
+static long g_stat_iters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define GG_STAT_TAG(k) g_stat_tag = (k);
 #include "../../gymgo_b200/csrc/gg_algo.cuh"
 
 namespace {
@@ -60,6 +63,7 @@ struct HostOps {
     P rev(P x) const { for (int j = 0; j < G::LPB; ++j) x.w[j] = gg::w_rev(x.w[j]); return x; }
     P hfill(P s, const P& m, const P& mrev) const {
         ++g_stat_hfill;
+        ++g_stat_iters[g_stat_tag & 7];
         for (int j = 0; j < G::LPB; ++j) s.w[j] = gg::w_hfill(s.w[j], m.w[j], mrev.w[j]);
         return s;
     }
@@ -188,6 +192,7 @@ struct Sim {
         HostOps<G> o;
         for (int b = 0; b < batch; ++b) {
             g_stat_hfill = g_stat_lowest = 0;
+            for (int k = 0; k < 8; ++k) g_stat_iters[k] = 0;
             HostPlane<G> bl, wh, iv;
             uint32_t flags;
             uint32_t* rec = recs + size_t(b) * G::REC_W32;
@@ -199,7 +204,10 @@ struct Sim {
             int a = gg::Algo<HostOps<G>>::sample_action(o, G(), iv, rnd);
             gg::Algo<HostOps<G>>::step(o, G(), bl, wh, iv, flags, a, 0u);
             rec_store<G>(rec, bl, wh, iv, flags);
-            if (stats) { stats[2 * b] = int32_t(g_stat_hfill); stats[2 * b + 1] = int32_t(g_stat_lowest); }
+            if (stats) {
+                stats[8 * b] = int32_t(g_stat_hfill); stats[8 * b + 1] = int32_t(g_stat_lowest);
+                for (int k = 0; k < 5; ++k) stats[8 * b + 2 + k] = int32_t(g_stat_iters[k]);
+            }
             if (actions) actions[b] = a;
         }
     }
@@ -259,7 +267,7 @@ int hs_rollout_step(int n, uint32_t* recs, int batch, uint64_t seed, uint64_t bo
     }
     return -1;
 }
-// developer statistics: stats[b] = {flood iterations, pocket-loop trips} of board b in this ply
+// developer statistics: stats[b][8] = {flood iterations, pocket-loop trips, iterations of flood kinds 0..4, -}
 int hs_rollout_step_stats(int n, uint32_t* recs, int batch, uint64_t seed, uint64_t board0, uint64_t t, int32_t* actions,
                           int32_t* stats) {
     switch (n) {
