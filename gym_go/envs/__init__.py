@@ -1,1 +1,1 @@
-from gymgo_b200.envs import GoEnv, GoExtraHardEnv, RewardMethod, BatchedGoEnv  # noqa: F401
+from gymgo_b200.envs import GoEnv, GoExtraHardEnv, RewardMethod, BatchedGoEnv, GoVectorEnv  # noqa: F401

@@ -45,7 +45,7 @@ def __getattr__(name):
     if name in ("gogame", "engine", "envs"):
         import importlib
         return importlib.import_module("." + name, __name__)
-    if name in ("BatchedGoEnv", "GoEnv", "GoExtraHardEnv"):
+    if name in ("BatchedGoEnv", "GoEnv", "GoExtraHardEnv", "GoVectorEnv"):
         from . import envs
         return getattr(envs, name)
     if name == "GoEngine":

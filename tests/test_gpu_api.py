@@ -183,3 +183,28 @@ def test_cuda_graph_capture_of_step_calls():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(rec, want_rec) and torch.equal(obs, want_obs)
+
+
+def test_vector_env_autoreset_and_masks():
+    from gymgo_b200.envs import GoVectorEnv
+    venv = GoVectorEnv(128, 5, reward_method="real", obs_dtype=torch.uint8, seed=4)
+    obs, info = venv.reset()
+    assert obs.shape == (128, 6, 5, 5) and not obs.any() and info["action_mask"].all()
+    ref = [og.EnvOracle(5) for _ in range(128)]
+    finished_before = np.zeros(128, dtype=bool)
+    ended = 0
+    for t in range(80):
+        acts = venv.sample_actions()
+        a = acts.cpu().numpy()
+        obs, rew, term, trunc, info = venv.step(acts)
+        assert not trunc.any() and not info["status"].any()
+        for i in range(128):
+            if finished_before[i]:
+                ref[i].reset()
+            s, r, d, _ = ref[i].step(int(a[i]))
+            assert np.array_equal(obs[i].cpu().numpy(), s.astype(np.uint8))
+            assert float(rew[i]) == float(r) and bool(term[i]) == bool(d)
+            assert np.array_equal(info["action_mask"][i].cpu().numpy(), og.valid_moves(s).astype(np.uint8))
+            finished_before[i] = bool(d)
+        ended += int(term.sum())
+    assert ended > 0
