@@ -1,6 +1,7 @@
 // gg_api.cu - the C ABI of include/gymgo_b200.h: argument checks + dispatch on the board size.
 // No allocation, no synchronisation, no global state besides the last-error string.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/gymgo_b200.h"
@@ -153,6 +154,9 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
     a.obs_ring = obs_ring_buf;
     a.obs_dtype = obs_dtype;
     a.ring = obs_ring_buf ? obs_ring : 1;
+    // developer switch (A/B measurements only): GG_ROLLOUT_VARIANT=1 selects the thread-per-board kernel on small boards
+    const char* variant = getenv("GG_ROLLOUT_VARIANT");
+    a.variant = variant ? atoi(variant) : 0;
     for (int p = 0; p < steps; p += plies_per_launch) {
         a.t0 = t0 + uint64_t(p);
         a.plies = steps - p < plies_per_launch ? steps - p : plies_per_launch;

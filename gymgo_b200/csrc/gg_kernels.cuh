@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "gg_algo.cuh"
+#include "gg_array_ops.cuh"
 
 namespace gg {
 
@@ -481,6 +482,7 @@ struct RolloutArgs {
     float komi;
     void* obs_ring;             // [ring, B, 6, N, N] or NULL; ply t writes slot t % ring
     int obs_dtype, ring;
+    int variant;                // 0: lane-sliced boards (k_rollout), 1: thread-per-board (k_rollout_tpb, small boards)
 };
 
 template <class G>
@@ -605,6 +607,156 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
         bulk_commit_wait_all();
     }
 }
+
+// =================================================================================================
+// Thread-per-board variant of the persistent rollout kernel for small boards (uint32 words, <= 3 words per
+// plane): the whole board lives in the registers of ONE thread (gg::ArrayOps), so the rules need no shuffles
+// and no ballots and a warp carries 32 boards; loops are thread-local (SIMT masks finished boards off).
+// Same staging (TMA bulk load/store of the record tile) and the same warp-private observation emission.
+// =================================================================================================
+template <class G>
+struct TpbTile {
+    static constexpr int THREADS = 64;                 // 2 warps: 1,024 CTAs for 65,536 boards (6.9 per SM)
+    static constexpr int BT = THREADS;
+    static constexpr int DENSE = 6 * G::NP;
+    static constexpr int WSTREAM_W32 = (32 * DENSE + 15 + 31) / 32 + 2;
+    static constexpr bool SUPPORTED = G::WB == 32 && G::LPB <= 3;
+};
+
+template <class G>
+__global__ void __launch_bounds__(TpbTile<G>::THREADS, 8) k_rollout_tpb(const RolloutArgs a) {
+    typedef typename G::W W;
+    typedef TpbTile<G> T;
+    typedef ArrayOps<G> O;
+    typedef ArrayPlane<G> P;
+    __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
+    __shared__ uint32_t s_bits_all[T::THREADS / 32][T::WSTREAM_W32];
+    __shared__ __align__(16) float4 s_lut[16];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile_base = (long long)blockIdx.x * T::BT;
+    const long long left = a.boards - tile_base;
+    const int nb = left < T::BT ? int(left) : T::BT;
+    const bool want_obs = a.obs_ring != nullptr;
+    uint32_t* s_bits = s_bits_all[warp];
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < 16) s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
+        bulk_g2s(s_rec, a.rec + tile_base * G::REC_W32, uint32_t(nb) * G::REC_BYTES, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const bool real = tid < nb;
+    const long long slot = tile_base + tid;
+    const O o(real);
+    uint32_t* my_rec = s_rec + tid * G::REC_W32;
+    P black = o.zero(), white = o.zero(), invd = o.zero();
+    uint32_t flags = 0;
+    if (real) {
+#pragma unroll
+        for (int j = 0; j < G::LPB; ++j) {
+            black.w[j] = rec_word<G>(my_rec, 0, j);
+            white.w[j] = rec_word<G>(my_rec, 1, j);
+            invd.w[j] = rec_word<G>(my_rec, 2, j);
+        }
+        flags = my_rec[G::FLAGS_IDX];
+    }
+
+    const long long wb0 = tile_base + warp * 32;
+    int nbw = nb - warp * 32;
+    nbw = nbw < 0 ? 0 : (nbw > 32 ? 32 : nbw);
+    const long long e0 = wb0 * T::DENSE;
+    const int align_mask = a.obs_dtype == DT_F32 ? 3 : 15;
+    const int count = nbw * T::DENSE;
+    const long long slot_elems = a.boards * T::DENSE;
+    const unsigned long long gb = a.board0 + (unsigned long long)slot;
+
+    for (int p = 0; p < a.plies; ++p) {
+        const unsigned long long t = a.t0 + (unsigned long long)p;
+        if (flags & FLAG_DONE) {
+            black = white = invd = o.zero();
+            flags = 0;
+        }
+        const uint32_t rnd = philox4x32_10(uint32_t(gb), uint32_t(gb >> 32), uint32_t(t), uint32_t(t >> 32),
+                                           uint32_t(a.seed), uint32_t(a.seed >> 32));
+        const int action = Algo<O>::sample_action(o, G(), invd, rnd);
+        Algo<O>::step(o, G(), black, white, invd, flags, action, 0u);
+
+        const bool over = (flags & FLAG_DONE) != 0;
+        const long long log_at = (long long)p * a.boards + slot;
+        if (real) {
+            if (a.actions_log) a.actions_log[log_at] = action;
+            if (a.done_log) a.done_log[log_at] = over ? 1 : 0;
+            if (a.reward_log) {
+                float r = 0.f;
+                if (a.reward_mode == 2 || over) {
+                    int ba, wa;
+                    Algo<O>::areas(o, black, white, ba, wa);
+                    const float diff = float(ba - wa) - a.komi;
+                    if (a.reward_mode == 1) r = over ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+                    else r = over ? (diff > 0.f ? float(G::NP) : -float(G::NP)) : diff;
+                }
+                a.reward_log[log_at] = r;
+            }
+        }
+        if (want_obs) {
+            const long long abs0 = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0;
+            const int head = int(abs0 & align_mask);
+            const long long at = abs0 - head;
+            __syncwarp();
+            for (int i = lane; i < T::WSTREAM_W32; i += 32) s_bits[i] = 0;
+            __syncwarp();
+            if (real) {
+#pragma unroll
+                for (int j = 0; j < G::LPB; ++j)
+                    stream_put_board<G>(s_bits, head + lane * T::DENSE, j, black.w[j], white.w[j], invd.w[j], flags);
+            }
+            __syncwarp();
+            if (a.obs_dtype == DT_F32) emit_f32<32>(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane);
+            else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
+            __syncwarp();
+        }
+    }
+
+    __syncwarp();
+    if (real) {
+#pragma unroll
+        for (int j = 0; j < G::LPB; ++j) {
+            rec_word_store<G>(my_rec, 0, j, black.w[j]);
+            rec_word_store<G>(my_rec, 1, j, white.w[j]);
+            rec_word_store<G>(my_rec, 2, j, invd.w[j]);
+        }
+        my_rec[G::FLAGS_IDX] = flags;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(a.rec + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
+        bulk_commit_wait_all();
+    }
+}
+
+inline unsigned blocks_for(long long items, int per_block) { return unsigned((items + per_block - 1) / per_block); }
+
+template <class G, bool OK = TpbTile<G>::SUPPORTED>
+struct LaunchTpb {
+    static void go(const RolloutArgs& a, cudaStream_t s) {
+        k_rollout_tpb<G><<<blocks_for(a.boards, TpbTile<G>::BT), TpbTile<G>::THREADS, 0, s>>>(a);
+    }
+};
+template <class G>
+struct LaunchTpb<G, false> {
+    static void go(const RolloutArgs& a, cudaStream_t s) {
+        k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
+    }
+};
 
 // ------------------------------------------------------------------ warp-layout helper kernels
 template <class G>
@@ -763,8 +915,6 @@ struct SizeVTable {
     cudaError_t (*canonical)(const uint32_t*, uint32_t*, long long, cudaStream_t);
 };
 
-inline unsigned blocks_for(long long items, int per_block) { return unsigned((items + per_block - 1) / per_block); }
-
 template <class G>
 struct Launch {
     static cudaError_t step(const StepArgs& a, int mode, cudaStream_t s) {
@@ -777,7 +927,8 @@ struct Launch {
     }
     static cudaError_t rollout(const RolloutArgs& a, cudaStream_t s) {
         if (a.boards <= 0 || a.plies <= 0) return cudaSuccess;
-        k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
+        if (a.variant == 1) LaunchTpb<G>::go(a, s);
+        else k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t areas(const uint32_t* rec, long long batch, int32_t* out, cudaStream_t s) {

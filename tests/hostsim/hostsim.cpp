@@ -10,93 +10,19 @@
 
 static int g_stat_tag = 0;
 static long g_stat_iters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// developer statistics (single-threaded test code): loop trips of the algorithm on the current board
+static long g_stat_hfill = 0, g_stat_lowest = 0;
 #define GG_STAT_TAG(k) g_stat_tag = (k);
-#include "../../gymgo_b200/csrc/gg_algo.cuh"
+#define GG_STAT_HFILL() (++g_stat_hfill, ++g_stat_iters[g_stat_tag & 7])
+#define GG_STAT_LOWEST() (++g_stat_lowest)
+#include "../../gymgo_b200/csrc/gg_array_ops.cuh"
 
 namespace {
 
-// developer statistics (single-threaded test code): loop trips of the algorithm on the current board
-static long g_stat_hfill = 0, g_stat_lowest = 0;
-
 template <class G>
-struct HostPlane {
-    typename G::W w[G::LPB];
-};
+using HostPlane = gg::ArrayPlane<G>;
 template <class G>
-inline HostPlane<G> operator|(HostPlane<G> a, const HostPlane<G>& b) {
-    for (int j = 0; j < G::LPB; ++j) a.w[j] |= b.w[j];
-    return a;
-}
-template <class G>
-inline HostPlane<G> operator&(HostPlane<G> a, const HostPlane<G>& b) {
-    for (int j = 0; j < G::LPB; ++j) a.w[j] &= b.w[j];
-    return a;
-}
-
-template <class G>
-struct HostOps {
-    typedef HostPlane<G> P;
-    typedef typename G::W W;
-    P zero() const { P p; for (int j = 0; j < G::LPB; ++j) p.w[j] = 0; return p; }
-    P full() const { P p; for (int j = 0; j < G::LPB; ++j) p.w[j] = G::rows_mask(G::rows_in_lane(j)); return p; }
-    P andnot(P a, const P& b) const { for (int j = 0; j < G::LPB; ++j) a.w[j] &= ~b.w[j]; return a; }
-    P east(P x) const { for (int j = 0; j < G::LPB; ++j) x.w[j] <<= 1; return x; }
-    P west(P x) const { for (int j = 0; j < G::LPB; ++j) x.w[j] >>= 1; return x; }
-    P south(const P& x) const {   // result[r] = x[r-1]
-        P y;
-        for (int j = 0; j < G::LPB; ++j) {
-            W in = G::RPL > 1 ? W(x.w[j] << (G::S % G::WB)) : W(0);
-            W prev = j ? W(x.w[j - 1] >> ((G::RPL - 1) * G::S)) : W(0);
-            y.w[j] = in | prev;
-        }
-        return y;
-    }
-    P north(const P& x) const {   // result[r] = x[r+1]
-        P y;
-        for (int j = 0; j < G::LPB; ++j) {
-            W in = G::RPL > 1 ? W(x.w[j] >> (G::S % G::WB)) : W(0);
-            W next = j + 1 < G::LPB ? W((x.w[j + 1] & G::row_bits()) << ((G::RPL - 1) * G::S)) : W(0);
-            y.w[j] = in | next;
-        }
-        return y;
-    }
-    P rev(P x) const { for (int j = 0; j < G::LPB; ++j) x.w[j] = gg::w_rev(x.w[j]); return x; }
-    P hfill(P s, const P& m, const P& mrev) const {
-        ++g_stat_hfill;
-        ++g_stat_iters[g_stat_tag & 7];
-        for (int j = 0; j < G::LPB; ++j) s.w[j] = gg::w_hfill(s.w[j], m.w[j], mrev.w[j]);
-        return s;
-    }
-    bool any_board(const P& x) const { W a = 0; for (int j = 0; j < G::LPB; ++j) a |= x.w[j]; return a != 0; }
-    bool any(const P& x) const { return any_board(x); }
-    int popc(const P& x) const { int c = 0; for (int j = 0; j < G::LPB; ++j) c += gg::w_popc(x.w[j]); return c; }
-    int count2(const P& x) const { int c = popc(x); return c > 2 ? 2 : c; }
-    P lowest(const P& x) const {
-        ++g_stat_lowest;
-        P y = zero();
-        for (int j = 0; j < G::LPB; ++j)
-            if (x.w[j]) { y.w[j] = x.w[j] & (~x.w[j] + 1); break; }
-        return y;
-    }
-    P single(int pt) const {
-        P y = zero();
-        int r = pt / G::N, c = pt % G::N;
-        y.w[r / G::RPL] = W(1) << ((r % G::RPL) * G::S + c);
-        return y;
-    }
-    P pick(bool c, const P& a, const P& b) const { return c ? a : b; }
-    int kth_point(const P& x, int k) const {
-        for (int j = 0; j < G::LPB; ++j) {
-            int c = gg::w_popc(x.w[j]);
-            if (k < c) {
-                int bit = gg::w_select(x.w[j], k);
-                return (j * G::RPL + bit / G::S) * G::N + bit % G::S;
-            }
-            k -= c;
-        }
-        return -1;
-    }
-};
+using HostOps = gg::ArrayOps<G>;
 
 // ---- record <-> planes, dense <-> planes (the record layout of gg_algo.cuh Geo<>) ----
 template <class G>

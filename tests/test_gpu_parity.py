@@ -177,6 +177,30 @@ def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
     assert all(bool((ring[s] == 7).all()) for s in untouched)
 
 
+@pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 40)))
+@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8))
+def test_thread_per_board_variant_matches(eng, n, boards, dtype, monkeypatch):
+    """the thread-per-board rollout kernel (developer variant for small boards) is bit-identical to the
+    lane-sliced one; sizes it does not support silently use the default kernel"""
+    e = eng(n)
+    outs = []
+    for variant in ("0", "1"):
+        monkeypatch.setenv("GG_ROLLOUT_VARIANT", variant)
+        rec = e.new_records(boards)
+        ring = e.empty((23, boards, 6, n, n), dtype=dtype)
+        ring.fill_(3)
+        acts = torch.empty((22, boards), dtype=torch.int32, device="cuda")
+        dones = torch.empty((22, boards), dtype=torch.uint8, device="cuda")
+        rews = torch.empty((22, boards), dtype=torch.float32, device="cuda")
+        e.rollout(rec, 5, 77, 0, 150, plies_per_launch=50)
+        e.rollout(rec, 5, 77, 150, 22, plies_per_launch=6, actions_log=acts, obs_ring=ring, done_log=dones,
+                  reward_log=rews, reward_mode=2, komi=1.5)
+        torch.cuda.synchronize()
+        outs.append((rec, ring, acts, dones, rews))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
 @pytest.mark.parametrize("n", golden_io.CHILDREN_SIZES)
 def test_children_golden(eng, n):
     e = eng(n)

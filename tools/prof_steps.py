@@ -1,6 +1,7 @@
 """Developer probe (not part of the product): per-ply kernel time as the game phase evolves, C-side vs Python
 launch loops, host launch overhead."""
 import json
+import os
 import sys
 import time
 
@@ -37,6 +38,14 @@ for size, boards in ((9, 65536), (19, 16384)):
     for k in (1, 2, 4, 8, 16, 50):
         ppl[k] = round(timed(lambda: eng.rollout(rec, 0, 0, t, 50, plies_per_launch=k, obs_ring=ring)) / 50, 2)
         t += 50
+    os.environ["GG_ROLLOUT_VARIANT"] = "1"
+    tpb = {}
+    for k in (1, 16, 50):
+        tpb[k] = round(timed(lambda: eng.rollout(rec, 0, 0, t, 50, plies_per_launch=k, obs_ring=ring)) / 50, 2)
+        t += 50
+    tpb["no_obs_16"] = round(timed(lambda: eng.rollout(rec, 0, 0, t, 48, plies_per_launch=16, obs_ring=None)) / 48, 2)
+    t += 48
+    os.environ["GG_ROLLOUT_VARIANT"] = "0"
     noobs = timed(lambda: eng.rollout(rec, 0, 0, t, 50, obs_ring=None)) / 50
     t += 50
     u8ring = eng.empty((3, boards, 6, size, size), dtype=torch.uint8)
@@ -54,6 +63,6 @@ for size, boards in ((9, 65536), (19, 16384)):
         eng.rollout_step(small, 0, 0, k)
     torch.cuda.synchronize()
     host = (time.time() - t0) / 2000 * 1e6
-    out["%dx%d" % (size, size)] = dict(us_per_ply_by_50=chunks, us_per_ply_by_plies_per_launch=ppl, no_obs_us=round(noobs, 2), u8_us=round(u8, 2),
+    out["%dx%d" % (size, size)] = dict(us_per_ply_by_50=chunks, us_per_ply_by_plies_per_launch=ppl, thread_per_board_variant=tpb, no_obs_us=round(noobs, 2), u8_us=round(u8, 2),
                                        python_loop_us=round(py, 2), host_call_us_tiny_batch=round(host, 2))
 print(json.dumps(out))
