@@ -331,7 +331,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(args.workload, args.obs, args.plies_per_launch),
-                         "algorithmic_bytes_per_launch": boards * bytes_per_ply * args.plies_per_launch, "kernel": "gg::k_rollout<Geo<%d>> (%d plies per launch)" % (size, args.plies_per_launch),
+                         "algorithmic_bytes_per_launch": boards * bytes_per_ply * args.plies_per_launch, "kernel": "gg::%s, Geo<%d>, %d plies per launch" % (eng.lib.gg_rollout_kernel(size, boards).decode(), size,
+                                                                              args.plies_per_launch),
                          "bytes_per_ply": bytes_per_ply, "peak_source": peak_src,
                          "launch_us": launch_s * 1e6},
         }

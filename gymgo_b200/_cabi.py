@@ -18,7 +18,7 @@ GG_STEP_CANONICAL, GG_STEP_REFUSE_DONE = 1, 2
 GG_REWARD_NONE, GG_REWARD_REAL, GG_REWARD_HEURISTIC = 0, 1, 2
 
 EXPORTS = ("gg_version", "gg_last_cuda_error", "gg_supported", "gg_set_device", "gg_layout", "gg_pack", "gg_unpack", "gg_reset",
-           "gg_step", "gg_rollout_step", "gg_rollout", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
+           "gg_step", "gg_rollout_step", "gg_rollout", "gg_rollout_kernel", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
            "gg_canonical")
 
 _ERR = {GG_EINVAL: "GG_EINVAL (bad argument)", GG_ESIZE: "GG_ESIZE (board size not supported, build has 2..19)",
@@ -56,6 +56,8 @@ def lib():
     L.gg_step.argtypes = [vp, vp, vp, vp, i64, i32, u32, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout_step.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout.argtypes = [vp, i64, i32, u64, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp, i32, f32, vp]
+    L.gg_rollout_kernel.argtypes = [i32, i64]
+    L.gg_rollout_kernel.restype = ctypes.c_char_p
     L.gg_sample_legal.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp]
     L.gg_valid_moves.argtypes = [vp, i64, i32, i32, i32, vp, vp]
     L.gg_children.argtypes = [vp, i64, i32, u32, vp, vp, i32, vp, vp, vp]

@@ -26,6 +26,16 @@ static const SizeVTable* lookup(int n) {
 
 static thread_local char g_err[256] = "";
 
+// Which persistent rollout kernel serves (n, batch): thread-per-board wins on small boards once the batch is
+// large enough to fill the SMs with one board per thread (measured: 9x9 x 65,536, profiles/r01_step_time_probe.json);
+// GG_ROLLOUT_VARIANT=0/1 overrides the choice for A/B measurements.
+static int rollout_variant(const SizeVTable* v, int64_t batch) {
+    const char* forced = getenv("GG_ROLLOUT_VARIANT");
+    const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
+    if (forced) return (atoi(forced) == 1 && tpb_ok) ? 1 : 0;
+    return (tpb_ok && batch >= 32768) ? 1 : 0;
+}
+
 static int finish(cudaError_t e) {
     if (e == cudaSuccess) return GG_OK;
     snprintf(g_err, sizeof g_err, "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -155,8 +165,7 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
     a.obs_dtype = obs_dtype;
     a.ring = obs_ring_buf ? obs_ring : 1;
     // developer switch (A/B measurements only): GG_ROLLOUT_VARIANT=1 selects the thread-per-board kernel on small boards
-    const char* variant = getenv("GG_ROLLOUT_VARIANT");
-    a.variant = variant ? atoi(variant) : 0;
+    a.variant = rollout_variant(v, batch);
     for (int p = 0; p < steps; p += plies_per_launch) {
         a.t0 = t0 + uint64_t(p);
         a.plies = steps - p < plies_per_launch ? steps - p : plies_per_launch;
@@ -167,6 +176,12 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
         if (e != cudaSuccess) return finish(e);
     }
     return GG_OK;
+}
+
+GG_API const char* gg_rollout_kernel(int n, int64_t batch) {
+    const SizeVTable* v = lookup(n);
+    if (!v) return "";
+    return rollout_variant(v, batch) == 1 ? "k_rollout_tpb (thread per board)" : "k_rollout (lane-sliced boards)";
 }
 
 GG_API int gg_sample_legal(const void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,

@@ -134,6 +134,10 @@ GG_API int gg_rollout(void *rec, int64_t batch, int n, uint64_t seed, uint64_t b
                       int plies_per_launch, int32_t *actions_log, void *obs_ring_buf, int obs_dtype, int obs_ring,
                       uint8_t *done_log, float *reward_log, int reward_mode, float komi, void *stream);
 
+/* Name of the kernel gg_rollout uses for (n, batch): small boards with large batches run one board per thread
+ * (k_rollout_tpb), everything else spreads a board over adjacent lanes (k_rollout).  Same results either way. */
+GG_API const char *gg_rollout_kernel(int n, int64_t batch);
+
 /* The sampler alone (no reset, no step): actions_out[b] = uniformly random valid action of board b.
  * Replaces: GoEnv.uniform_random_action / gogame.random_action (go_env.py:78-81, gogame.py:395-404). */
 GG_API int gg_sample_legal(const void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,
