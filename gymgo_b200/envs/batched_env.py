@@ -35,11 +35,14 @@ class BatchedGoEnv(object):
     # gym-style API ----------------------------------------------------------------------------
     def reset(self, mask=None):
         """all boards (or those with mask != 0) back to the empty position; returns observations"""
+        if mask is not None:
+            mask = torch.as_tensor(np.asarray(mask) if not isinstance(mask, torch.Tensor) else mask)
+            mask = mask.to(self.done.device).ne(0)
         self.engine.reset(self.rec, mask)
         if mask is None:
             self.done.zero_()
         else:
-            self.done.masked_fill_(torch.as_tensor(mask).to(self.done.device).bool(), 0)
+            self.done.masked_fill_(mask, 0)
         return self.engine.unpack(self.rec, out=self.obs)
 
     def step(self, actions, auto_reset=False):
