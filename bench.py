@@ -294,6 +294,27 @@ def run_ours(args, wl, rank, world, local_rank):
     if e2e_steps == K and not torch.equal(env.rec, final_rec):
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
 
+    # ---------------- informational: the same host-driven loop when the observation stays on the device (the
+    # consumer is a device-resident policy network): actions H2D, reward + done D2H, synchronised every step
+    env.reset()
+
+    def e2e_ply_light(t):
+        a_dev.copy_(actions_host[t], non_blocking=True)
+        _, r, d, _ = env.step(a_dev, auto_reset=True)
+        rew_host.copy_(r, non_blocking=True)
+        done_host.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    light_steps = min(e2e_steps, W + K)
+    torch.cuda.synchronize()
+    ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev6.record()
+    for t in range(light_steps):
+        e2e_ply_light(t)
+    ev7.record()
+    torch.cuda.synchronize()
+    light_secs = ev6.elapsed_time(ev7) / 1e3
+
     # ---------------- gather (plies, seconds) of every rank: the only collective of the job
     from gymgo_b200 import sharding
     allr = sharding.gather_counters([float(boards) * K, secs, float(boards) * e2e_steps, e2e_secs], device=dev)
@@ -323,7 +344,11 @@ def run_ours(args, wl, rank, world, local_rank):
                     "h2d_bytes_per_step": boards * 4 * world,
                     "d2h_bytes_per_step": (dense_bytes + boards * 5) * world, "steps": e2e_steps,
                     "api": "BatchedGoEnv.step(actions, auto_reset=True): pinned-host actions in; %s observation, reward, "
-                           "done out to pinned host, stream-synchronised every step" % args.obs},
+                           "done out to pinned host, stream-synchronised every step" % args.obs,
+                    "obs_kept_on_device": {"value": boards * light_steps * world / light_secs, "unit": "env-steps/s",
+                                           "d2h_bytes_per_step": boards * 5 * world,
+                                           "note": "rank-0 timing of the same loop when only reward + done go back to "
+                                                   "the host (observation consumed on the device); informational"}},
             "gpu_launches": -(-K // args.plies_per_launch),
             "one_launch_per_ply": {"value": boards * n1 * world / one_ply_secs, "ms_per_step": 1e3 * one_ply_secs / n1,
                                    "note": "rank-0 timing of the same kernel with plies_per_launch=1 (records reloaded "
