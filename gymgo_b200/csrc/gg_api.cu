@@ -32,7 +32,7 @@ static thread_local char g_err[256] = "";
 static int rollout_variant(const SizeVTable* v, int64_t batch) {
     const char* forced = getenv("GG_ROLLOUT_VARIANT");
     const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
-    if (forced) return (atoi(forced) == 1 && tpb_ok) ? 1 : 0;
+    if (forced) return atoi(forced) == 1 ? 1 : 0;
     return (tpb_ok && batch >= 32768) ? 1 : 0;
 }
 

@@ -609,22 +609,23 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
 }
 
 // =================================================================================================
-// Thread-per-board variant of the persistent rollout kernel for small boards (uint32 words, <= 3 words per
-// plane): the whole board lives in the registers of ONE thread (gg::ArrayOps), so the rules need no shuffles
+// Thread-per-board variant of the persistent rollout kernel: the whole board lives in the registers of ONE thread (gg::ArrayOps), so the rules need no shuffles
 // and no ballots and a warp carries 32 boards; loops are thread-local (SIMT masks finished boards off).
 // Same staging (TMA bulk load/store of the record tile) and the same warp-private observation emission.
 // =================================================================================================
 template <class G>
 struct TpbTile {
-    static constexpr int THREADS = 64;                 // 2 warps: 1,024 CTAs for 65,536 boards (6.9 per SM)
+    // small boards: 2 warps per CTA (1,024 CTAs for 65,536 boards = 6.9 per SM, 91 registers);
+    // uint64 boards: 1 warp per CTA with up to 255 registers per thread (19x19: 243, no spills)
+    static constexpr int THREADS = G::WB == 32 ? 64 : 32;
+    static constexpr int MIN_BLOCKS = G::WB == 32 ? 8 : 4;
     static constexpr int BT = THREADS;
     static constexpr int DENSE = 6 * G::NP;
     static constexpr int WSTREAM_W32 = (32 * DENSE + 15 + 31) / 32 + 2;
-    static constexpr bool SUPPORTED = G::WB == 32 && G::LPB <= 3;
 };
 
 template <class G>
-__global__ void __launch_bounds__(TpbTile<G>::THREADS, 8) k_rollout_tpb(const RolloutArgs a) {
+__global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k_rollout_tpb(const RolloutArgs a) {
     typedef typename G::W W;
     typedef TpbTile<G> T;
     typedef ArrayOps<G> O;
@@ -745,16 +746,10 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, 8) k_rollout_tpb(const Ro
 
 inline unsigned blocks_for(long long items, int per_block) { return unsigned((items + per_block - 1) / per_block); }
 
-template <class G, bool OK = TpbTile<G>::SUPPORTED>
+template <class G>
 struct LaunchTpb {
     static void go(const RolloutArgs& a, cudaStream_t s) {
         k_rollout_tpb<G><<<blocks_for(a.boards, TpbTile<G>::BT), TpbTile<G>::THREADS, 0, s>>>(a);
-    }
-};
-template <class G>
-struct LaunchTpb<G, false> {
-    static void go(const RolloutArgs& a, cudaStream_t s) {
-        k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
     }
 };
 

@@ -177,11 +177,10 @@ def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
     assert all(bool((ring[s] == 7).all()) for s in untouched)
 
 
-@pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 40)))
+@pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 141), (13, 97), (16, 33)))
 @pytest.mark.parametrize("dtype", (torch.float32, torch.uint8))
 def test_thread_per_board_variant_matches(eng, n, boards, dtype, monkeypatch):
-    """the thread-per-board rollout kernel (developer variant for small boards) is bit-identical to the
-    lane-sliced one; sizes it does not support silently use the default kernel"""
+    """the thread-per-board rollout kernel is bit-identical to the lane-sliced one (GG_ROLLOUT_VARIANT forces either)"""
     e = eng(n)
     outs = []
     for variant in ("0", "1"):
