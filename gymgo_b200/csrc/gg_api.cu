@@ -32,7 +32,7 @@ static thread_local char g_err[256] = "";
 static int rollout_variant(const SizeVTable* v, int64_t batch) {
     const char* forced = getenv("GG_ROLLOUT_VARIANT");
     const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
-    if (forced) return atoi(forced) == 1 ? 1 : 0;
+    if (forced) return atoi(forced);
     return (tpb_ok && batch >= 32768) ? 1 : 0;
 }
 
@@ -166,6 +166,8 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
     a.ring = obs_ring_buf ? obs_ring : 1;
     // developer switch (A/B measurements only): GG_ROLLOUT_VARIANT=1 selects the thread-per-board kernel on small boards
     a.variant = rollout_variant(v, batch);
+    const char* slice_k = getenv("GG_ROLLOUT_K");
+    a.slice_k = slice_k ? atoi(slice_k) : 2;
     for (int p = 0; p < steps; p += plies_per_launch) {
         a.t0 = t0 + uint64_t(p);
         a.plies = steps - p < plies_per_launch ? steps - p : plies_per_launch;
@@ -181,7 +183,9 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
 GG_API const char* gg_rollout_kernel(int n, int64_t batch) {
     const SizeVTable* v = lookup(n);
     if (!v) return "";
-    return rollout_variant(v, batch) == 1 ? "k_rollout_tpb (thread per board)" : "k_rollout (lane-sliced boards)";
+    const int variant = rollout_variant(v, batch);
+    return variant == 1 ? "k_rollout_tpb (thread per board)"
+                        : (variant == 2 ? "k_rollout_sliced (several words per lane)" : "k_rollout (lane-sliced boards)");
 }
 
 GG_API int gg_sample_legal(const void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,

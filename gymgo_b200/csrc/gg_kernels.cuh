@@ -482,7 +482,9 @@ struct RolloutArgs {
     float komi;
     void* obs_ring;             // [ring, B, 6, N, N] or NULL; ply t writes slot t % ring
     int obs_dtype, ring;
-    int variant;                // 0: lane-sliced boards (k_rollout), 1: thread-per-board (k_rollout_tpb, small boards)
+    int variant;                // 0: one word per lane (k_rollout), 1: thread-per-board (k_rollout_tpb),
+                                // 2: slice_k words per lane (k_rollout_sliced, gg_sliced.cuh)
+    int slice_k;
 };
 
 template <class G>
@@ -920,10 +922,12 @@ struct Launch {
         else k_step<G, MODE_CHILDREN><<<grid, Tile<G>::THREADS, 0, s>>>(a);
         return cudaGetLastError();
     }
+    static bool launch_sliced(const RolloutArgs& a, cudaStream_t s);   // defined in gg_size.cu (needs gg_sliced.cuh)
     static cudaError_t rollout(const RolloutArgs& a, cudaStream_t s) {
         if (a.boards <= 0 || a.plies <= 0) return cudaSuccess;
         if (a.variant == 1) LaunchTpb<G>::go(a, s);
-        else k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
+        else if (!(a.variant == 2 && launch_sliced(a, s)))
+            k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t areas(const uint32_t* rec, long long batch, int32_t* out, cudaStream_t s) {

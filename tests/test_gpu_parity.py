@@ -200,6 +200,29 @@ def test_thread_per_board_variant_matches(eng, n, boards, dtype, monkeypatch):
         assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("n,boards,k", ((19, 141, 2), (19, 77, 3), (19, 50, 4), (13, 97, 2), (16, 33, 3), (11, 200, 2)))
+def test_sliced_variant_matches(eng, n, boards, k, monkeypatch):
+    """k_rollout_sliced (K plane words per lane, developer variant 2) is bit-identical to the default kernel"""
+    e = eng(n)
+    outs = []
+    for variant in ("0", "2"):
+        monkeypatch.setenv("GG_ROLLOUT_VARIANT", variant)
+        monkeypatch.setenv("GG_ROLLOUT_K", str(k))
+        rec = e.new_records(boards)
+        ring = e.empty((9, boards, 6, n, n), dtype=torch.float32)
+        ring.fill_(3)
+        acts = torch.empty((22, boards), dtype=torch.int32, device="cuda")
+        dones = torch.empty((22, boards), dtype=torch.uint8, device="cuda")
+        rews = torch.empty((22, boards), dtype=torch.float32, device="cuda")
+        e.rollout(rec, 5, 77, 0, 250, plies_per_launch=50)
+        e.rollout(rec, 5, 77, 250, 22, plies_per_launch=6, actions_log=acts, obs_ring=ring, done_log=dones,
+                  reward_log=rews, reward_mode=1, komi=0.5)
+        torch.cuda.synchronize()
+        outs.append((rec, ring, acts, dones, rews))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
 @pytest.mark.parametrize("n", golden_io.CHILDREN_SIZES)
 def test_children_golden(eng, n):
     e = eng(n)

@@ -45,6 +45,19 @@ for size, boards in ((9, 65536), (19, 16384)):
         t += 50
     tpb["no_obs_16"] = round(timed(lambda: eng.rollout(rec, 0, 0, t, 48, plies_per_launch=16, obs_ring=None)) / 48, 2)
     t += 48
+    sliced = {}
+    if size > 9:
+        os.environ["GG_ROLLOUT_VARIANT"] = "2"
+        for k in (2, 3, 4):
+            os.environ["GG_ROLLOUT_K"] = str(k)
+            a = round(timed(lambda: eng.rollout(rec, 0, 0, t, 48, plies_per_launch=16, obs_ring=ring)) / 48, 2)
+            b = round(timed(lambda: eng.rollout(rec, 0, 0, t, 48, plies_per_launch=16, obs_ring=None)) / 48, 2)
+            os.environ["GG_ROLLOUT_VARIANT"] = "0"
+            c = round(timed(lambda: eng.rollout(rec, 0, 0, t, 48, plies_per_launch=16, obs_ring=ring)) / 48, 2)
+            d = round(timed(lambda: eng.rollout(rec, 0, 0, t, 48, plies_per_launch=16, obs_ring=None)) / 48, 2)
+            os.environ["GG_ROLLOUT_VARIANT"] = "2"
+            sliced[k] = dict(obs=a, no_obs=b, default_same_phase_obs=c, default_same_phase_no_obs=d)
+            t += 48
     os.environ["GG_ROLLOUT_VARIANT"] = "0"
     noobs = timed(lambda: eng.rollout(rec, 0, 0, t, 50, obs_ring=None)) / 50
     t += 50
@@ -63,6 +76,6 @@ for size, boards in ((9, 65536), (19, 16384)):
         eng.rollout_step(small, 0, 0, k)
     torch.cuda.synchronize()
     host = (time.time() - t0) / 2000 * 1e6
-    out["%dx%d" % (size, size)] = dict(us_per_ply_by_50=chunks, us_per_ply_by_plies_per_launch=ppl, thread_per_board_variant=tpb, no_obs_us=round(noobs, 2), u8_us=round(u8, 2),
+    out["%dx%d" % (size, size)] = dict(us_per_ply_by_50=chunks, us_per_ply_by_plies_per_launch=ppl, thread_per_board_variant=tpb, sliced_variant=sliced, no_obs_us=round(noobs, 2), u8_us=round(u8, 2),
                                        python_loop_us=round(py, 2), host_call_us_tiny_batch=round(host, 2))
 print(json.dumps(out))
