@@ -210,6 +210,21 @@ struct Algo {
     }
     static GG_HD P flood(const O& o, P seed, P mask) { return flood(o, seed, mask, o.rev(mask)); }
 
+    // two independent floods advanced together: one vote per iteration instead of two and two independent
+    // dependency chains for the scheduler to interleave (the iteration count is the larger of the two)
+    static GG_HD void flood2(const O& o, P& x1, P m1, P& x2, P m2) {
+        const P r1 = o.rev(m1), r2 = o.rev(m2);
+        for (;;) {
+            x1 = o.hfill(x1, m1, r1);
+            x2 = o.hfill(x2, m2, r2);
+            const P v1 = o.andnot((o.south(x1) | o.north(x1)) & m1, x1);
+            const P v2 = o.andnot((o.south(x2) | o.north(x2)) & m2, x2);
+            if (!o.any(v1 | v2)) break;
+            x1 = x1 | v1;
+            x2 = x2 | v2;
+        }
+    }
+
     // INVD plane for the player whose stones are `nxt` (to move), `oth` = the player who just moved.
     // invalid(p) = occupied | ko | ( no empty neighbour
     //                                & not adjacent to an `oth` group with exactly one liberty
@@ -232,9 +247,8 @@ struct Algo {
             const P two = (ee & ew) | (es & en) | ((ee | ew) & (es | en));   // touches >= 2 empty points
             const P healthy = nbrs(o, open) | two;
             GG_STAT_TAG(2)
-            const P big_nxt = flood(o, nxt & healthy, nxt);                // groups with >= 2 liberties (sufficient)
-            GG_STAT_TAG(3)
-            const P big_oth = flood(o, oth & healthy, oth);
+            P big_nxt = nxt & healthy, big_oth = oth & healthy;             // -> groups with >= 2 liberties (sufficient)
+            flood2(o, big_nxt, nxt, big_oth, oth);
             bad = o.andnot(bad, nbrs(o, big_nxt));     // own group with >= 2 liberties: safe
             const P rest_nxt = o.andnot(nxt, big_nxt);
             const P rest_oth = o.andnot(oth, big_oth);
@@ -336,8 +350,8 @@ struct Algo {
     // Tromp-Taylor areas: stones + empty points reachable (through empties) from one colour only.
     static GG_HD void areas(const O& o, P black, P white, int& black_area, int& white_area) {
         const P empty = o.andnot(o.full(), black | white);
-        const P rb = flood(o, nbrs(o, black) & empty, empty);
-        const P rw = flood(o, nbrs(o, white) & empty, empty);
+        P rb = nbrs(o, black) & empty, rw = nbrs(o, white) & empty;
+        flood2(o, rb, empty, rw, empty);
         black_area = o.popc(black | o.andnot(rb, rw));
         white_area = o.popc(white | o.andnot(rw, rb));
     }
