@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--boards", type=int, default=None, help="boards per GPU (default: the workload's)")
     ap.add_argument("--obs", default="f32", choices=["f32", "u8"])
     ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--plies-per-launch", type=int, default=16,
+    ap.add_argument("--plies-per-launch", type=int, default=32,
                     help="plies the persistent rollout kernel plays per launch (boards stay in registers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -138,7 +138,7 @@ class GoEngine(object):
                                              _ptr(actions), _ptr(obs), _TORCH2GG[obs.dtype] if obs is not None else 0,
                                              _ptr(done), _ptr(areas), _ptr(reward), int(reward_mode), float(komi), s))
 
-    def rollout(self, rec, seed, board0, t0, steps, plies_per_launch=16, actions_log=None, obs_ring=None,
+    def rollout(self, rec, seed, board0, t0, steps, plies_per_launch=32, actions_log=None, obs_ring=None,
                 done_log=None, reward_log=None, reward_mode=0, komi=0.0):
         """`steps` fused rollout plies by the persistent kernel (gg_rollout), `plies_per_launch` plies per launch.
         obs_ring: [R,B,6,N,N] ring of observation slots (ply t writes slot t % R); actions_log int32 [steps,B],
