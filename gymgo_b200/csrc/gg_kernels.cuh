@@ -21,7 +21,7 @@
 namespace gg {
 
 enum { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_CHILDREN = 2 };
-enum { DT_U8 = 0, DT_F32 = 1, DT_F64 = 2, DT_NONE = -1 };
+enum { DT_U8 = 0, DT_F32 = 1, DT_F64 = 2 };
 
 struct StepArgs {
     const uint32_t* rec_in;     // STEP/ROLLOUT: [B] records; CHILDREN: [B] parent records

@@ -44,10 +44,9 @@ class GoEngine(object):
 
     # ------------------------------------------------------------------ plumbing
     def _enter(self):
-        """make this engine's device current for torch's and the library's CUDA runtime; returns the stream"""
+        """Bind the LIBRARY's own (statically linked) CUDA runtime to this engine's device for the calling thread and
+        return torch's current stream on that device.  torch's notion of the current device is left untouched."""
         idx = self.device.index
-        if torch.cuda.current_device() != idx:
-            torch.cuda.set_device(idx)
         if getattr(_tls, "device", None) != idx:
             _cabi.check(self.lib.gg_set_device(idx))
             _tls.device = idx
