@@ -44,9 +44,15 @@ class GoEngine(object):
 
     # ------------------------------------------------------------------ plumbing
     def _enter(self):
-        """Bind the LIBRARY's own (statically linked) CUDA runtime to this engine's device for the calling thread and
-        return torch's current stream on that device.  torch's notion of the current device is left untouched."""
+        """Make this engine's device current and return torch's current stream on it.
+        The library links its own CUDA runtime, but the "current device" is a property of the thread's driver
+        context that both runtimes follow (measured: gg_set_device(1) moves torch.cuda.current_device() to 1), so,
+        like torch.cuda.set_device, this switches the calling thread to the engine's device and leaves it there.
+        One process per GPU (the intended deployment) never notices."""
         idx = self.device.index
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
+            _tls.device = None
         if getattr(_tls, "device", None) != idx:
             _cabi.check(self.lib.gg_set_device(idx))
             _tls.device = idx
