@@ -26,23 +26,17 @@ static const SizeVTable* lookup(int n) {
 
 static thread_local char g_err[256] = "";
 
-// Which persistent rollout kernel serves (n, batch): thread-per-board wins on small boards once the batch is
-// large enough to fill the SMs with one board per thread (measured: 9x9 x 65,536, profiles/r01_step_time_probe.json);
-// GG_ROLLOUT_VARIANT=0/1 overrides the choice for A/B measurements.
+// Which persistent rollout kernel serves (n, batch).  Measured (profiles/r01_variant_threshold.json, f32
+// observations): both kernels sit within a few percent of the pure-write floor; thread-per-board is ahead by up
+// to 5 % on small boards around 64 Ki boards (the lane-sliced kernel cannot fully overlap rules and stores there),
+// behind below 32 Ki (too few warps) and level or slightly behind at 128 Ki (both write-bound).
+// GG_ROLLOUT_VARIANT=0/1/2 overrides the choice for A/B measurements.
 static int rollout_variant(const SizeVTable* v, int64_t batch) {
     const char* forced = getenv("GG_ROLLOUT_VARIANT");
-    const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
     if (forced) return atoi(forced);
-    return (tpb_ok && batch >= 32768) ? 1 : 0;
+    const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
+    return (tpb_ok && batch >= 49152 && batch < 98304) ? 1 : 0;
 }
-
-static int finish(cudaError_t e) {
-    if (e == cudaSuccess) return GG_OK;
-    snprintf(g_err, sizeof g_err, "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
-    return GG_ECUDA;
-}
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static bool dense_dtype_ok(int dt, bool allow_f64) { return dt == GG_U8 || dt == GG_F32 || (allow_f64 && dt == GG_F64); }
 }  // namespace gg
 
 using namespace gg;
