@@ -70,7 +70,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -218,14 +218,31 @@ def run_ours(args, wl, rank, world, local_rank):
     nbuf = max(2, int(-(-300e6 // dense_bytes)))
     obs_ring = eng.empty((nbuf, boards, 6, size, size), dtype=obs_dtype)
     rec = eng.new_records(boards)
-    actions_log = torch.empty((W + K, boards), dtype=torch.int32, device=dev)
-    reward_log = torch.empty((W + K, boards), dtype=torch.float32, device=dev)
-    done_log = torch.empty((W + K, boards), dtype=torch.uint8, device=dev)
+    # The e2e leg replays the first W + E plies of this very rollout from host memory, so their actions are
+    # recorded; later plies log into a reusable chunk (reward / done are always logged, like an RL loop needs).
+    E = min(K, 300) if args.e2e_steps is None else min(K, args.e2e_steps)
+    CHUNK = 256
+    actions_replay = torch.empty((W + E, boards), dtype=torch.int32, device=dev)
+    actions_chunk = torch.empty((CHUNK, boards), dtype=torch.int32, device=dev)
+    reward_chunk = torch.empty((CHUNK, boards), dtype=torch.float32, device=dev)
+    done_chunk = torch.empty((CHUNK, boards), dtype=torch.uint8, device=dev)
+    ppl = args.plies_per_launch
 
     def plies(t0, count):
-        # ONE C call (gg_rollout): persistent kernel, args.plies_per_launch plies per launch, boards in registers
-        eng.rollout(rec, SEED, board0, t0, count, plies_per_launch=args.plies_per_launch, actions_log=actions_log[t0:],
-                    obs_ring=obs_ring, done_log=done_log[t0:], reward_log=reward_log[t0:], reward_mode=1, komi=0.0)
+        """gg_rollout (persistent kernel, `ppl` plies per launch, boards in registers) in calls of <= CHUNK plies"""
+        launches, t, end = 0, t0, t0 + count
+        while t < end:
+            n = min(CHUNK, end - t)
+            if t < W + E:
+                n = min(n, W + E - t)
+                alog = actions_replay[t:]
+            else:
+                alog = actions_chunk
+            eng.rollout(rec, SEED, board0, t, n, plies_per_launch=ppl, actions_log=alog, obs_ring=obs_ring,
+                        done_log=done_chunk, reward_log=reward_chunk, reward_mode=1, komi=0.0)
+            launches += -(-n // ppl)
+            t += n
+        return launches
 
     def barrier():
         if world > 1:
@@ -242,13 +259,15 @@ def run_ours(args, wl, rank, world, local_rank):
     barrier()
     wall0 = time.time()
     ev0.record()
-    plies(W, K)
+    n_launches = plies(W, K)
     ev1.record()
     barrier()
     wall1 = time.time()
     secs = ev0.elapsed_time(ev1) / 1e3
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    final_rec = rec.clone()
+    # reference state for the e2e replay check: the rollout after exactly W + E plies (deterministic re-run, untimed)
+    final_rec = eng.new_records(boards)
+    eng.rollout(final_rec, SEED, board0, 0, W + E, plies_per_launch=ppl)
 
     # ---------------- transparency: the same plies with ONE launch per ply (no register residency across plies)
     scratch = rec.clone()
@@ -257,15 +276,15 @@ def run_ours(args, wl, rank, world, local_rank):
     eng.rollout(scratch, SEED, board0, W + K, 8, plies_per_launch=1, obs_ring=obs_ring)
     torch.cuda.synchronize()
     ev4.record()
-    eng.rollout(scratch, SEED, board0, W + K + 8, n1, plies_per_launch=1, obs_ring=obs_ring, done_log=done_log,
-                reward_log=reward_log, reward_mode=1, komi=0.0)     # (actions_log is kept intact for the e2e replay)
+    eng.rollout(scratch, SEED, board0, W + K + 8, n1, plies_per_launch=1, obs_ring=obs_ring, done_log=done_chunk,
+                reward_log=reward_chunk, actions_log=actions_chunk, reward_mode=1, komi=0.0)
     ev5.record()
     torch.cuda.synchronize()
     one_ply_secs = ev4.elapsed_time(ev5) / 1e3
 
     # ---------------- e2e: the public BatchedGoEnv.step with HOST buffers, copies inside the timed region
-    actions_host = torch.empty((W + K, boards), dtype=torch.int32, pin_memory=True)
-    actions_host.copy_(actions_log)
+    actions_host = torch.empty((W + E, boards), dtype=torch.int32, pin_memory=True)
+    actions_host.copy_(actions_replay)
     env = BatchedGoEnv(boards, size, reward_method="real", device=dev, obs_dtype=obs_dtype, board_offset=board0)
     obs_host = torch.empty((boards, 6, size, size), dtype=obs_dtype, pin_memory=True)
     rew_host = torch.empty((boards,), dtype=torch.float32, pin_memory=True)
@@ -280,7 +299,7 @@ def run_ours(args, wl, rank, world, local_rank):
         done_host.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()                           # the host now owns the result
 
-    e2e_steps = K if args.e2e_steps is None else min(K, args.e2e_steps)
+    e2e_steps = E
     for t in range(W):
         e2e_ply(t)
     barrier()
@@ -291,7 +310,7 @@ def run_ours(args, wl, rank, world, local_rank):
     ev3.record()
     barrier()
     e2e_secs = ev2.elapsed_time(ev3) / 1e3
-    if e2e_steps == K and not torch.equal(env.rec, final_rec):
+    if not torch.equal(env.rec, final_rec):
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
 
     # ---------------- informational: the same host-driven loop when the observation stays on the device (the
@@ -305,7 +324,7 @@ def run_ours(args, wl, rank, world, local_rank):
         done_host.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    light_steps = min(e2e_steps, W + K)
+    light_steps = min(e2e_steps, W + E)
     torch.cuda.synchronize()
     ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev6.record()
@@ -324,7 +343,6 @@ def run_ours(args, wl, rank, world, local_rank):
         value = total_plies / t_max
         bytes_per_ply = algorithmic_bytes_per_ply(size, obs_elem)
         peak, peak_src = measured_peak_gbs()
-        n_launches = -(-K // args.plies_per_launch)
         launch_s = float(allr[0, 1]) / n_launches                      # average duration of one kernel launch
         achieved = boards * bytes_per_ply * (K / float(n_launches)) / launch_s / 1e9
         line = {
@@ -349,7 +367,7 @@ def run_ours(args, wl, rank, world, local_rank):
                                            "d2h_bytes_per_step": boards * 5 * world,
                                            "note": "rank-0 timing of the same loop when only reward + done go back to "
                                                    "the host (observation consumed on the device); informational"}},
-            "gpu_launches": -(-K // args.plies_per_launch),
+            "gpu_launches": n_launches,
             "one_launch_per_ply": {"value": boards * n1 * world / one_ply_secs, "ms_per_step": 1e3 * one_ply_secs / n1,
                                    "note": "rank-0 timing of the same kernel with plies_per_launch=1 (records reloaded "
                                            "and stored every ply)"},
@@ -381,7 +399,8 @@ def run_ours(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=10000,
+                    help="timed plies (default 10,000 = about a quarter second per GPU, long enough to sample clocks)")
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="9x9", choices=sorted(WORKLOADS))
