@@ -242,4 +242,13 @@ GG_API int gg_canonical(const void* rec_in, void* rec_out, int64_t batch, int n,
                                static_cast<cudaStream_t>(stream)));
 }
 
+GG_API int gg_symmetry(const void* rec_in, void* rec_out, int64_t batch, int n, int sym, void* stream) {
+    const SizeVTable* v = lookup(n);
+    if (!v) return GG_ESIZE;
+    if (batch < 0 || sym < 0 || sym > 7 || (batch > 0 && (!rec_in || !rec_out || rec_in == rec_out))) return GG_EINVAL;
+    if (!aligned16(rec_in) || !aligned16(rec_out)) return GG_EALIGN;
+    return finish(v->symmetry(static_cast<const uint32_t*>(rec_in), static_cast<uint32_t*>(rec_out), batch, sym,
+                              static_cast<cudaStream_t>(stream)));
+}
+
 }  // extern "C"

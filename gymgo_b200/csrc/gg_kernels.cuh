@@ -897,6 +897,43 @@ __global__ void k_canonical(const uint32_t* in, uint32_t* out, long long batch) 
     w[G::FLAGS_IDX] = flags & ~uint32_t(FLAG_TURN);
 }
 
+// One of the 8 dihedral transforms on packed records (gogame.all_symmetries order: s = 4*flip + k, i.e.
+// np.rot90(np.flip(x, -1) if flip else x, k)); one thread per (board, plane word), flags copied.
+template <class G>
+__global__ void k_symmetry(const uint32_t* in, uint32_t* out, long long batch, int sym) {
+    constexpr int UNITS = 3 * G::LPB + 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batch * UNITS) return;
+    const long long b = gid / UNITS;
+    const int u = int(gid - b * UNITS);
+    const uint32_t* r = in + b * G::REC_W32;
+    uint32_t* w = out + b * G::REC_W32;
+    if (u == 3 * G::LPB) {
+        for (int i = G::FLAGS_IDX; i < G::REC_W32; ++i) w[i] = r[i];
+        return;
+    }
+    const int plane = u / G::LPB, j = u - plane * G::LPB;
+    const int k = sym & 3;
+    const bool flip = (sym & 4) != 0;
+    typename G::W word = 0;
+    const int rows = G::rows_in_lane(j);
+    for (int i = 0; i < rows; ++i) {
+        const int row = j * G::RPL + i;
+        for (int c = 0; c < G::N; ++c) {
+            int a, d;                                   // source point in the (possibly flipped) base image
+            if (k == 0) { a = row; d = c; }
+            else if (k == 1) { a = c; d = G::N - 1 - row; }
+            else if (k == 2) { a = G::N - 1 - row; d = G::N - 1 - c; }
+            else { a = G::N - 1 - c; d = row; }
+            if (flip) d = G::N - 1 - d;
+            const int sj = a / G::RPL;
+            const typename G::W src = rec_word<G>(r, plane, sj);
+            if ((src >> ((a - sj * G::RPL) * G::S + d)) & 1) word |= typename G::W(1) << (i * G::S + c);
+        }
+    }
+    rec_word_store<G>(w, plane, j, word);
+}
+
 // ------------------------------------------------------------------------------ launch table
 struct SizeVTable {
     int n, rec_bytes, lpb, rpl, wordbits, bpw, tile_boards, tile_threads;
@@ -910,6 +947,7 @@ struct SizeVTable {
     cudaError_t (*valid)(const uint32_t*, long long, int quirk, int dtype, void*, cudaStream_t);
     cudaError_t (*reset)(uint32_t*, long long, const uint8_t*, cudaStream_t);
     cudaError_t (*canonical)(const uint32_t*, uint32_t*, long long, cudaStream_t);
+    cudaError_t (*symmetry)(const uint32_t*, uint32_t*, long long, int, cudaStream_t);
 };
 
 template <class G>
@@ -976,9 +1014,14 @@ struct Launch {
         k_canonical<G><<<blocks_for(batch, 128), 128, 0, s>>>(in, out, batch);
         return cudaGetLastError();
     }
+    static cudaError_t symmetry(const uint32_t* in, uint32_t* out, long long batch, int sym, cudaStream_t s) {
+        if (batch <= 0) return cudaSuccess;
+        k_symmetry<G><<<blocks_for(batch * (3 * G::LPB + 1), 256), 256, 0, s>>>(in, out, batch, sym);
+        return cudaGetLastError();
+    }
     static constexpr SizeVTable table() {
         return SizeVTable{G::N, G::REC_BYTES, G::LPB, G::RPL, G::WB, G::BPW, Tile<G>::BT, Tile<G>::THREADS,
-                          &step, &rollout, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical};
+                          &step, &rollout, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical, &symmetry};
     }
 };
 

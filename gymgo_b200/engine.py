@@ -201,6 +201,14 @@ class GoEngine(object):
         _cabi.check(self.lib.gg_canonical(_ptr(rec), _ptr(out), rec.shape[0], self.size, s))
         return out
 
+    def symmetry(self, rec, sym):
+        """packed records transformed by dihedral symmetry `sym` (0..7, the order of gogame.all_symmetries)"""
+        self._check_rec(rec)
+        out = torch.empty_like(rec)
+        s = self._enter()
+        _cabi.check(self.lib.gg_symmetry(_ptr(rec), _ptr(out), rec.shape[0], self.size, int(sym), s))
+        return out
+
     # flags word of every record as int32 [B]: bit0 turn, bit1 previous pass, bit2 game over
     def flags(self, rec):
         self._check_rec(rec)

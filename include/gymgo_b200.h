@@ -166,6 +166,11 @@ GG_API int gg_areas(const void *rec, int64_t batch, int n, int32_t *out, void *s
  * Replaces: gogame.canonical_form / batch_canonical_form (gogame.py:313-337). */
 GG_API int gg_canonical(const void *rec_in, void *rec_out, int64_t batch, int n, void *stream);
 
+/* One of the 8 dihedral transforms applied to packed records (stone and invalid planes; flags copied), out of
+ * place.  sym = 4*flip + k reproduces element `sym` of gogame.all_symmetries (gogame.py:358-382):
+ * np.rot90(np.flip(x, -1) if flip else x, k).  Replaces: random_symmetry / all_symmetries (gogame.py:340-382). */
+GG_API int gg_symmetry(const void *rec_in, void *rec_out, int64_t batch, int n, int sym, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ def test_header_symbols_are_exported():
     from gymgo_b200 import _cabi
     lib = _cabi.lib()
     names = declared_symbols()
-    assert len(names) >= 17 and set(names) == set(_cabi.EXPORTS)
+    assert len(names) >= 18 and set(names) == set(_cabi.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
     assert lib.gg_version() == 100

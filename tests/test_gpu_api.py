@@ -208,3 +208,17 @@ def test_vector_env_autoreset_and_masks():
             finished_before[i] = bool(d)
         ended += int(term.sum())
     assert ended > 0
+
+
+@pytest.mark.parametrize("n", (5, 9, 13, 19))
+def test_packed_symmetries_match_numpy(n):
+    from gymgo_b200 import gogame
+    from gymgo_b200.engine import GoEngine
+    from test_device_algo_hostsim import random_soup
+    e = GoEngine(n, "cuda:0")
+    st = random_soup(n, 50, np.random.RandomState(n))
+    rec = e.pack(torch.from_numpy(st).cuda())
+    want = gogame.all_symmetries(st)
+    for sym in range(8):
+        got = e.unpack(e.symmetry(rec, sym), dtype=torch.uint8).cpu().numpy()
+        assert np.array_equal(got, want[sym]), sym
