@@ -59,6 +59,9 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
+    for stale in (LIB, os.path.join(LIBDIR, "digest.txt")):      # never leave a stale library behind a failed build
+        if os.path.exists(stale):
+            os.remove(stale)
     cc = nvcc()
     jobs = []
     for n in SIZES:

@@ -37,6 +37,14 @@ static int rollout_variant(const SizeVTable* v, int64_t batch) {
     const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
     return (tpb_ok && batch >= 49152 && batch < 98304) ? 1 : 0;
 }
+
+static int finish(cudaError_t e) {
+    if (e == cudaSuccess) return GG_OK;
+    snprintf(g_err, sizeof g_err, "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return GG_ECUDA;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool dense_dtype_ok(int dt, bool allow_f64) { return dt == GG_U8 || dt == GG_F32 || (allow_f64 && dt == GG_F64); }
 }  // namespace gg
 
 using namespace gg;
