@@ -127,22 +127,6 @@ GG_HD int w_ctz(uint64_t x) {
     return __builtin_ctzll(x);
 #endif
 }
-// the highest set bit of x as a one-bit word (0 if x == 0)
-GG_HD uint32_t w_top(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-    return x ? 0x80000000u >> __clz(int(x)) : 0u;
-#else
-    return x ? 0x80000000u >> __builtin_clz(x) : 0u;
-#endif
-}
-GG_HD uint64_t w_top(uint64_t x) {
-#if defined(__CUDA_ARCH__)
-    return x ? 0x8000000000000000ull >> __clzll((long long)x) : 0ull;
-#else
-    return x ? 0x8000000000000000ull >> __builtin_clzll(x) : 0ull;
-#endif
-}
-
 // position of the k-th (0-based) set bit of x; requires k < popc(x).  Branch-light binary search on
 // popcounts of the low halves (5 / 6 rounds) instead of clearing k bits one by one.
 GG_HD int w_select(uint32_t x, int k) {
@@ -200,7 +184,7 @@ GG_HD uint32_t philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 //   bool any_board(P)              this board has a bit
 //   int  count2(P)                 min(popcount over this board, 2)
 //   int  popc(P)                   popcount over this board
-//   P lowest(P), highest(P)        only the lowest / highest set point of this board (empty if none)
+//   P lowest(P)                    only the lowest set point of this board (empty if none)
 //   P single(int pt)               plane with point pt (row-major index) set; pt must be in range
 //   P pick(bool c, P a, P b)       c ? a : b
 //   int kth_point(P x, int k)      row-major index of the k-th (0-based) set point of this board, k < popc(x)
@@ -228,7 +212,8 @@ struct Algo {
 
     // two independent floods advanced together: one vote per iteration instead of two and two independent
     // dependency chains for the scheduler to interleave (the iteration count is the larger of the two)
-    static GG_HD void flood2(const O& o, P& x1, P m1, P r1, P& x2, P m2, P r2) {
+    static GG_HD void flood2(const O& o, P& x1, P m1, P& x2, P m2) {
+        const P r1 = o.rev(m1), r2 = o.rev(m2);
         for (;;) {
             x1 = o.hfill(x1, m1, r1);
             x2 = o.hfill(x2, m2, r2);
@@ -239,7 +224,6 @@ struct Algo {
             x2 = x2 | v2;
         }
     }
-    static GG_HD void flood2(const O& o, P& x1, P m1, P& x2, P m2) { flood2(o, x1, m1, o.rev(m1), x2, m2, o.rev(m2)); }
 
     // INVD plane for the player whose stones are `nxt` (to move), `oth` = the player who just moved.
     // invalid(p) = occupied | ko | ( no empty neighbour
@@ -276,21 +260,16 @@ struct Algo {
                 bad = o.andnot(bad, nbrs(o, lone_oth));
                 P todo = (o.andnot(cand_nxt, lone_nxt) | o.andnot(cand_oth, lone_oth)) & nbrs(o, bad);
                 const P rrev_nxt = o.rev(rest_nxt), rrev_oth = o.rev(rest_oth);
-                // two groups per trip (the lowest and the highest stone still to do): one shared vote and two
-                // independent dependency chains; if both stones belong to one group the work is merely duplicated
                 while (o.any(todo)) {
+                    const P s = o.lowest(todo);
+                    const bool mine = o.any_board(s & nxt);
                     GG_STAT_TAG(4)
-                    P g1 = o.lowest(todo), g2 = o.highest(todo);
-                    const bool mine1 = o.any_board(g1 & nxt);
-                    const bool mine2 = o.any_board(g2 & nxt);
-                    flood2(o, g1, o.pick(mine1, rest_nxt, rest_oth), o.pick(mine1, rrev_nxt, rrev_oth),
-                           g2, o.pick(mine2, rest_nxt, rest_oth), o.pick(mine2, rrev_nxt, rrev_oth));
-                    const P libs1 = nbrs(o, g1) & empty, libs2 = nbrs(o, g2) & empty;
-                    const int n1 = o.count2(libs1), n2 = o.count2(libs2);
-                    const bool ok1 = mine1 ? (n1 >= 2) : (n1 == 1);       // stays alive / captures
-                    const bool ok2 = mine2 ? (n2 >= 2) : (n2 == 1);
-                    bad = o.andnot(bad, o.pick(ok1, libs1, o.zero()) | o.pick(ok2, libs2, o.zero()));
-                    todo = o.andnot(todo, g1 | g2) & nbrs(o, bad);
+                    const P grp = flood(o, s, o.pick(mine, rest_nxt, rest_oth), o.pick(mine, rrev_nxt, rrev_oth));
+                    const P libs = nbrs(o, grp) & empty;
+                    const int nl = o.count2(libs);
+                    const bool playable = mine ? (nl >= 2) : (nl == 1);   // stays alive / captures
+                    bad = o.andnot(bad, o.pick(playable, libs, o.zero()));
+                    todo = o.andnot(todo, grp) & nbrs(o, bad);
                 }
             }
         }

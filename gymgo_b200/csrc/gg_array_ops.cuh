@@ -120,15 +120,6 @@ struct ArrayOps {
         }
         return y;
     }
-    GG_HD P highest(const P& x) const {
-        P y;
-        bool found = false;
-        GG_UNROLL for (int j = G::LPB - 1; j >= 0; --j) {
-            y.w[j] = found ? W(0) : w_top(x.w[j]);
-            found = found || x.w[j] != 0;
-        }
-        return y;
-    }
     GG_HD P single(int pt) const {
         const int r = pt / G::N, c = pt - r * G::N;
         const int lj = r / G::RPL;

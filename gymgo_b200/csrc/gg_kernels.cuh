@@ -153,12 +153,6 @@ struct DevOps {
         const unsigned nz = group_ballot(x != 0);
         return (j == __ffs(int(nz)) - 1) ? low : W(0);
     }
-    __device__ __forceinline__ P highest(P x) const {
-        const W top = w_top(x);
-        if (G::LPB == 1) return top;
-        const unsigned nz = group_ballot(x != 0);
-        return (nz != 0 && j == 31 - __clz(int(nz))) ? top : W(0);
-    }
     __device__ __forceinline__ P single(int pt) const {
         const int r = pt / G::N, c = pt - r * G::N;
         const int lj = r / G::RPL;

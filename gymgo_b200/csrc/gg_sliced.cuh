@@ -163,21 +163,6 @@ struct SlicedOps {
         }
         return y;
     }
-    __device__ __forceinline__ P highest(const P& x) const {
-        bool mine = true;
-        if (S::L > 1) {
-            const unsigned nz = group_ballot(fold(x) != 0);
-            mine = nz != 0 && j == 31 - __clz(int(nz));
-        }
-        P y;
-        bool found = !mine;
-#pragma unroll
-        for (int i = K - 1; i >= 0; --i) {
-            y.w[i] = found ? W(0) : w_top(x.w[i]);
-            found = found || x.w[i] != 0;
-        }
-        return y;
-    }
     __device__ __forceinline__ P single(int pt) const {
         const int r = pt / G::N, c = pt - r * G::N;
         const int g = r / G::RPL;                                  // global word
