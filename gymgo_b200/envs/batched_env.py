@@ -13,9 +13,11 @@ _REWARD = {"real": _cabi.GG_REWARD_REAL, "heuristic": _cabi.GG_REWARD_HEURISTIC}
 
 class BatchedGoEnv(object):
     def __init__(self, batch_size, size, komi=0, reward_method="real", device=None, obs_dtype=torch.float32,
-                 strict=False, seed=0, board_offset=0):
+                 strict=False, seed=0, board_offset=0, use_cuda_graph=False):
         """board_offset: global index of board 0 (so that rollouts are identical however the global batch is
-        sharded over GPUs); strict: raise AssertionError when any board refuses its action."""
+        sharded over GPUs); strict: raise AssertionError when any board refuses its action;
+        use_cuda_graph: step() replays a captured CUDA graph (reset + ply kernels) instead of enqueuing the
+        launches from Python - the C ABI only enqueues work on the caller's stream, so it is capturable."""
         if reward_method not in _REWARD:
             raise ValueError("reward_method must be 'real' or 'heuristic'")
         self.engine = GoEngine(size, device)
@@ -29,6 +31,8 @@ class BatchedGoEnv(object):
         self.done = e.empty((self.batch_size,))
         self.status = e.empty((self.batch_size,))
         self.actions = e.empty((self.batch_size,), dtype=torch.int32)
+        self._step_actions = e.empty((self.batch_size,), dtype=torch.int32)    # static input of step() (graph-safe)
+        self.use_cuda_graph, self._graphs = bool(use_cuda_graph), {}
         self.t = 0
         self.reset()
 
@@ -45,23 +49,55 @@ class BatchedGoEnv(object):
             self.done.masked_fill_(mask, 0)
         return self.engine.unpack(self.rec, out=self.obs)
 
+    @property
+    def action_buffer(self):
+        """the env's static int32 [B] action tensor: fill it (e.g. copy_ from pinned host memory) and pass it to
+        step() to avoid an extra device copy"""
+        return self._step_actions
+
+    def _enqueue_step(self, auto_reset):
+        """enqueue (optional reset of finished boards) + one ply on torch's current stream; inputs/outputs are the
+        env's static tensors, so the same sequence can be captured into a CUDA graph"""
+        e = self.engine
+        s = e._enter()
+        if auto_reset:
+            _cabi.check(e.lib.gg_reset(self.rec.data_ptr(), self.batch_size, self.size, self.done.data_ptr(), s))
+        _cabi.check(e.lib.gg_step(self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(),
+                                  self.status.data_ptr(), self.batch_size, self.size, _cabi.GG_STEP_REFUSE_DONE,
+                                  self.obs.data_ptr(), _cabi.GG_U8 if self.obs_dtype == torch.uint8 else _cabi.GG_F32,
+                                  self.done.data_ptr(), None, self.reward.data_ptr(), self.reward_mode,
+                                  float(self.komi), s))
+
+    def _graph(self, auto_reset):
+        g = self._graphs.get(auto_reset)
+        if g is None:
+            # make sure both kernels are loaded before capturing (lazy module loading): run them on a scratch board
+            scratch = BatchedGoEnv(1, self.size, device=self.engine.device, obs_dtype=self.obs_dtype)
+            scratch._step_actions.fill_(self.size * self.size)
+            scratch._enqueue_step(True)
+            torch.cuda.synchronize(self.engine.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_step(auto_reset)
+            self._graphs[auto_reset] = g
+        return g
+
     def step(self, actions, auto_reset=False):
         """actions: int [B] (N*N = pass) -> (obs [B,6,N,N], reward [B] f32, done [B] u8, info).
         Finished boards refuse to step (status 3, GoEnv's `assert not self.done`) until reset;
         auto_reset=True first resets the boards that finished on the previous step (vector-env style)."""
         a = self.engine._actions(actions, self.batch_size)
-        e = self.engine
-        s = e._enter()
-        if auto_reset:
-            _cabi.check(e.lib.gg_reset(self.rec.data_ptr(), self.batch_size, self.size, self.done.data_ptr(), s))
-        _cabi.check(e.lib.gg_step(self.rec.data_ptr(), a.data_ptr(), self.rec.data_ptr(), self.status.data_ptr(),
-                                  self.batch_size, self.size, _cabi.GG_STEP_REFUSE_DONE, self.obs.data_ptr(),
-                                  _cabi.GG_U8 if self.obs_dtype == torch.uint8 else _cabi.GG_F32,
-                                  self.done.data_ptr(), None, self.reward.data_ptr(), self.reward_mode,
-                                  float(self.komi), s))
+        if a.data_ptr() != self._step_actions.data_ptr():
+            self._step_actions.copy_(a, non_blocking=True)
+        if self.use_cuda_graph:
+            self.engine._enter()
+            self._graph(bool(auto_reset)).replay()
+        else:
+            self._enqueue_step(auto_reset)
         if self.strict and bool(self.status.any()):
             i = int(torch.nonzero(self.status)[0])
-            raise AssertionError(("refused action", int(a[i]), "board %d" % i, "status %d" % int(self.status[i])))
+            raise AssertionError(("refused action", int(self._step_actions[i]), "board %d" % i,
+                                  "status %d" % int(self.status[i])))
         return self.obs, self.reward, self.done, {"status": self.status}
 
     def random_step(self):

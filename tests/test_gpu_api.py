@@ -222,3 +222,17 @@ def test_packed_symmetries_match_numpy(n):
     for sym in range(8):
         got = e.unpack(e.symmetry(rec, sym), dtype=torch.uint8).cpu().numpy()
         assert np.array_equal(got, want[sym]), sym
+
+
+def test_batched_env_cuda_graph_step_equals_eager():
+    from gymgo_b200.envs import BatchedGoEnv
+    eager = BatchedGoEnv(3000, 9, reward_method="heuristic", komi=0.5, obs_dtype=torch.uint8)
+    graph = BatchedGoEnv(3000, 9, reward_method="heuristic", komi=0.5, obs_dtype=torch.uint8, use_cuda_graph=True)
+    for t in range(150):
+        acts = eager.engine.sample_legal(eager.rec, 9, 0, t)
+        reset = t % 3 != 0
+        oe, re_, de, ie = eager.step(acts, auto_reset=reset)
+        og_, rg, dg, ig = graph.step(acts.clone(), auto_reset=reset)
+        assert torch.equal(oe, og_) and torch.equal(re_, rg) and torch.equal(de, dg)
+        assert torch.equal(ie["status"], ig["status"])
+    assert torch.equal(eager.rec, graph.rec) and bool(eager.done.any())
