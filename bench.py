@@ -315,13 +315,11 @@ def run_ours(args, wl, rank, world, local_rank):
 
     # ---------------- informational: the same host-driven loop when the observation stays on the device (the
     # consumer is a device-resident policy network): actions H2D, reward + done D2H, synchronised every step
-    genv = BatchedGoEnv(boards, size, reward_method="real", device=dev, obs_dtype=obs_dtype, board_offset=board0,
-                        use_cuda_graph=True)                                # step() = one CUDA-graph replay
-    g_dev = genv.action_buffer
+    env.reset()
 
     def e2e_ply_light(t):
-        g_dev.copy_(actions_host[t], non_blocking=True)
-        _, r, d, _ = genv.step(g_dev, auto_reset=True)
+        a_dev.copy_(actions_host[t], non_blocking=True)
+        _, r, d, _ = env.step(a_dev, auto_reset=True)
         rew_host.copy_(r, non_blocking=True)
         done_host.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -368,8 +366,7 @@ def run_ours(args, wl, rank, world, local_rank):
                     "obs_kept_on_device": {"value": boards * light_steps * world / light_secs, "unit": "env-steps/s",
                                            "d2h_bytes_per_step": boards * 5 * world,
                                            "note": "rank-0 timing of the same loop when only reward + done go back to "
-                                                   "the host (observation consumed on the device) and step() replays a "
-                                                   "captured CUDA graph (use_cuda_graph=True); informational"}},
+                                                   "the host (observation consumed on the device); informational"}},
             "gpu_launches": n_launches,
             "one_launch_per_ply": {"value": boards * n1 * world / one_ply_secs, "ms_per_step": 1e3 * one_ply_secs / n1,
                                    "note": "rank-0 timing of the same kernel with plies_per_launch=1 (records reloaded "
