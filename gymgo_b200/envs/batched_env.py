@@ -32,7 +32,7 @@ class BatchedGoEnv(object):
         self.status = e.empty((self.batch_size,))
         self.actions = e.empty((self.batch_size,), dtype=torch.int32)
         self._step_actions = e.empty((self.batch_size,), dtype=torch.int32)    # static input of step() (graph-safe)
-        self.use_cuda_graph, self._graphs = bool(use_cuda_graph), {}
+        self.use_cuda_graph, self._graphs, self._c_args = bool(use_cuda_graph), {}, None
         self.t = 0
         self.reset()
 
@@ -57,16 +57,21 @@ class BatchedGoEnv(object):
 
     def _enqueue_step(self, auto_reset):
         """enqueue (optional reset of finished boards) + one ply on torch's current stream; inputs/outputs are the
-        env's static tensors, so the same sequence can be captured into a CUDA graph"""
+        env's static tensors, so the argument lists are built once and the same sequence can be captured into a
+        CUDA graph"""
         e = self.engine
         s = e._enter()
+        if self._c_args is None:
+            self._c_args = (
+                (self.rec.data_ptr(), self.batch_size, self.size, self.done.data_ptr()),
+                (self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(), self.status.data_ptr(),
+                 self.batch_size, self.size, _cabi.GG_STEP_REFUSE_DONE, self.obs.data_ptr(),
+                 _cabi.GG_U8 if self.obs_dtype == torch.uint8 else _cabi.GG_F32, self.done.data_ptr(), None,
+                 self.reward.data_ptr(), self.reward_mode, float(self.komi)))
+        reset_args, step_args = self._c_args
         if auto_reset:
-            _cabi.check(e.lib.gg_reset(self.rec.data_ptr(), self.batch_size, self.size, self.done.data_ptr(), s))
-        _cabi.check(e.lib.gg_step(self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(),
-                                  self.status.data_ptr(), self.batch_size, self.size, _cabi.GG_STEP_REFUSE_DONE,
-                                  self.obs.data_ptr(), _cabi.GG_U8 if self.obs_dtype == torch.uint8 else _cabi.GG_F32,
-                                  self.done.data_ptr(), None, self.reward.data_ptr(), self.reward_mode,
-                                  float(self.komi), s))
+            _cabi.check(e.lib.gg_reset(*reset_args, s))
+        _cabi.check(e.lib.gg_step(*step_args, s))
 
     def _graph(self, auto_reset):
         g = self._graphs.get(auto_reset)
@@ -86,9 +91,10 @@ class BatchedGoEnv(object):
         """actions: int [B] (N*N = pass) -> (obs [B,6,N,N], reward [B] f32, done [B] u8, info).
         Finished boards refuse to step (status 3, GoEnv's `assert not self.done`) until reset;
         auto_reset=True first resets the boards that finished on the previous step (vector-env style)."""
-        a = self.engine._actions(actions, self.batch_size)
-        if a.data_ptr() != self._step_actions.data_ptr():
-            self._step_actions.copy_(a, non_blocking=True)
+        if actions is not self._step_actions:                       # (passing env.action_buffer skips all of this)
+            a = self.engine._actions(actions, self.batch_size)
+            if a.data_ptr() != self._step_actions.data_ptr():
+                self._step_actions.copy_(a, non_blocking=True)
         if self.use_cuda_graph:
             self.engine._enter()
             self._graph(bool(auto_reset)).replay()
