@@ -207,8 +207,8 @@ def run_ours(args, wl, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     size, boards = wl["size"], args.boards or wl["boards"]
-    obs_dtype = torch.float32 if args.obs == "f32" else torch.uint8
-    obs_elem = 4 if args.obs == "f32" else 1
+    obs_dtype = {"f32": torch.float32, "u8": torch.uint8, "bf16": torch.bfloat16}[args.obs]
+    obs_elem = {"f32": 4, "u8": 1, "bf16": 2}[args.obs]
     eng = GoEngine(size, dev)
     board0 = rank * boards
     K, W = args.steps, args.warmup
@@ -405,7 +405,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="9x9", choices=sorted(WORKLOADS))
     ap.add_argument("--boards", type=int, default=None, help="boards per GPU (default: the workload's)")
-    ap.add_argument("--obs", default="f32", choices=["f32", "u8"])
+    ap.add_argument("--obs", default="f32", choices=["f32", "u8", "bf16"])
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--plies-per-launch", type=int, default=32,
                     help="plies the persistent rollout kernel plays per launch (boards stay in registers)")

@@ -12,7 +12,7 @@ _LIB = None
 # return codes / enums of include/gymgo_b200.h
 GG_OK, GG_EINVAL, GG_ESIZE, GG_EALIGN, GG_ECUDA = 0, -1, -2, -3, -4
 GG_ST_OK, GG_ST_INVALID_MOVE, GG_ST_OUT_OF_RANGE, GG_ST_GAME_OVER = 0, 1, 2, 3
-GG_U8, GG_F32, GG_F64 = 0, 1, 2
+GG_U8, GG_F32, GG_F64, GG_BF16, GG_F16 = 0, 1, 2, 3, 4
 GG_STEP_CANONICAL, GG_STEP_REFUSE_DONE = 1, 2
 
 GG_REWARD_NONE, GG_REWARD_REAL, GG_REWARD_HEURISTIC = 0, 1, 2

@@ -44,7 +44,9 @@ static int finish(cudaError_t e) {
     return GG_ECUDA;
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static bool dense_dtype_ok(int dt, bool allow_f64) { return dt == GG_U8 || dt == GG_F32 || (allow_f64 && dt == GG_F64); }
+static bool dense_dtype_ok(int dt, bool allow_f64) {
+    return dt == GG_U8 || dt == GG_F32 || dt == GG_BF16 || dt == GG_F16 || (allow_f64 && dt == GG_F64);
+}
 }  // namespace gg
 
 using namespace gg;
@@ -203,7 +205,7 @@ GG_API int gg_sample_legal(const void* rec, int64_t batch, int n, uint64_t seed,
 GG_API int gg_valid_moves(const void* rec, int64_t batch, int n, int ended_quirk, int dtype, void* out, void* stream) {
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
-    if (batch < 0 || !dense_dtype_ok(dtype, true) || (batch > 0 && (!rec || !out))) return GG_EINVAL;
+    if (batch < 0 || !(dtype == GG_U8 || dtype == GG_F32 || dtype == GG_F64) || (batch > 0 && (!rec || !out))) return GG_EINVAL;
     if (!aligned16(rec)) return GG_EALIGN;
     return finish(v->valid(static_cast<const uint32_t*>(rec), batch, ended_quirk, dtype, out, static_cast<cudaStream_t>(stream)));
 }

@@ -21,7 +21,7 @@
 namespace gg {
 
 enum { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_CHILDREN = 2 };
-enum { DT_U8 = 0, DT_F32 = 1, DT_F64 = 2 };
+enum { DT_U8 = 0, DT_F32 = 1, DT_F64 = 2, DT_BF16 = 3, DT_F16 = 4 };
 
 struct StepArgs {
     const uint32_t* rec_in;     // STEP/ROLLOUT: [B] records; CHILDREN: [B] parent records
@@ -296,6 +296,55 @@ __device__ __forceinline__ void emit_u8(const uint32_t* s_bits, int head, int co
     }
 }
 
+// 16-bit floats (bf16 / f16): 8 elements per 16-byte vector; one stream byte -> two table lookups (4 halves each).
+template <int NT>
+__device__ __forceinline__ void emit_h16(const uint32_t* s_bits, const uint2* s_lut, int head, int count, uint16_t* base,
+                                         int tid, uint16_t one) {
+    static_assert(NT % 32 == 0, "stride must keep the byte position fixed per thread");
+    const int end = head + count;
+    const int q_lo = (head + 7) >> 3, q_hi = end >> 3;             // full vectors are [q_lo, q_hi)
+    uint4* base4 = reinterpret_cast<uint4*>(base);
+    const int sh = (tid & 3) << 3;
+    int q = tid;
+    if (q < q_lo) q += NT;
+    const uint32_t* w = s_bits + (q >> 2);
+    uint4* g = base4 + q;
+#pragma unroll 4
+    for (; q < q_hi; q += NT, w += NT / 4, g += NT) {
+        const uint32_t byte = (*w >> sh) & 255u;
+        const uint2 lo = s_lut[byte & 15u], hi = s_lut[byte >> 4];
+        __stcs(g, make_uint4(lo.x, lo.y, hi.x, hi.y));
+    }
+    if (tid < 16) {                                                 // the (at most two) partial vectors
+        const int e = tid < 8 ? tid : (q_hi << 3) + tid - 8;
+        if (e >= head && e < end && (e < (q_lo << 3) || e >= (q_hi << 3)))
+            base[e] = ((s_bits[e >> 5] >> (e & 31)) & 1u) ? one : uint16_t(0);
+    }
+}
+
+// dtype dispatch shared by every kernel that writes observations
+__device__ __forceinline__ uint16_t obs_one16(int dt) { return dt == DT_BF16 ? uint16_t(0x3F80) : uint16_t(0x3C00); }
+__device__ __forceinline__ int obs_align_mask(int dt) { return dt == DT_F32 ? 3 : (dt == DT_U8 ? 15 : 7); }
+__device__ __forceinline__ void obs_lut_init(float4* s_lut, int dt, int tid) {
+    if (tid >= 16) return;
+    if (dt == DT_BF16 || dt == DT_F16) {
+        const uint32_t one = obs_one16(dt);
+        reinterpret_cast<uint2*>(s_lut)[tid] =
+            make_uint2(((tid & 1) ? one : 0u) | ((tid & 2) ? one << 16 : 0u), ((tid & 4) ? one : 0u) | ((tid & 8) ? one << 16 : 0u));
+    } else {
+        s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    }
+}
+// expand stream bits [head, head+count) into the dense buffer `buf` starting at element index `at` (16-byte aligned)
+template <int NT>
+__device__ __forceinline__ void emit_obs(int dt, const uint32_t* s_bits, const float4* s_lut, int head, int count, void* buf,
+                                         long long at, int tid) {
+    if (dt == DT_F32) emit_f32<NT>(s_bits, s_lut, head, count, static_cast<float*>(buf) + at, tid);
+    else if (dt == DT_U8) emit_u8(s_bits, head, count, static_cast<uint8_t*>(buf) + at, tid, NT);
+    else emit_h16<NT>(s_bits, reinterpret_cast<const uint2*>(s_lut), head, count, static_cast<uint16_t*>(buf) + at, tid,
+                      obs_one16(dt));
+}
+
 // =================================================================================================
 // The hot kernel: one ply for a tile of boards (STEP), fused reset+sample+ply (ROLLOUT), or one child
 // per (parent, action) slot (CHILDREN).
@@ -323,8 +372,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     }
     if (want_obs) {
         for (int i = tid; i < T::STREAM_W32; i += T::THREADS) s_bits[i] = 0;
-        if (tid < 16)
-            s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+        obs_lut_init(s_lut, a.obs_dtype, tid);
     }
     __syncthreads();
     if (MODE != MODE_CHILDREN) {
@@ -457,8 +505,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     if (want_obs) {
         const int elems = nb * T::DENSE;
         const long long ebase = tile_base * T::DENSE;
-        if (a.obs_dtype == DT_F32) emit_f32<T::THREADS>(s_bits, s_lut, 0, elems, static_cast<float*>(a.obs) + ebase, tid);
-        else emit_u8(s_bits, 0, elems, static_cast<uint8_t*>(a.obs) + ebase, tid, T::THREADS);
+        emit_obs<T::THREADS>(a.obs_dtype, s_bits, s_lut, 0, elems, a.obs, ebase, tid);
     }
     if (a.rec_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -514,7 +561,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    if (tid < 16) s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    obs_lut_init(s_lut, a.obs_dtype, tid);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
@@ -546,7 +593,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     int nbw = nb - warp * G::BPW;
     nbw = nbw < 0 ? 0 : (nbw > G::BPW ? G::BPW : nbw);
     const long long e0 = wb0 * WS::DENSE;                          // first element inside an observation slot
-    const int align_mask = a.obs_dtype == DT_F32 ? 3 : 15;         // elements per 16-byte vector, minus 1
+    const int align_mask = obs_align_mask(a.obs_dtype);            // elements per 16-byte vector, minus 1
     const int count = nbw * WS::DENSE;
     const long long slot_elems = a.boards * WS::DENSE;
     const unsigned long long gb = a.board0 + (unsigned long long)slot;
@@ -589,8 +636,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
             __syncwarp();
             if (holder) stream_put_board<G>(s_bits, head + slot_in_warp * WS::DENSE, j, black, white, invd, flags);
             __syncwarp();
-            if (a.obs_dtype == DT_F32) emit_f32<32>(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane);
-            else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
+            emit_obs<32>(a.obs_dtype, s_bits, s_lut, head, count, a.obs_ring, at, lane);
             __syncwarp();
         }
     }
@@ -648,7 +694,7 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    if (tid < 16) s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    obs_lut_init(s_lut, a.obs_dtype, tid);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
@@ -676,7 +722,7 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
     int nbw = nb - warp * 32;
     nbw = nbw < 0 ? 0 : (nbw > 32 ? 32 : nbw);
     const long long e0 = wb0 * T::DENSE;
-    const int align_mask = a.obs_dtype == DT_F32 ? 3 : 15;
+    const int align_mask = obs_align_mask(a.obs_dtype);
     const int count = nbw * T::DENSE;
     const long long slot_elems = a.boards * T::DENSE;
     const unsigned long long gb = a.board0 + (unsigned long long)slot;
@@ -722,8 +768,7 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
                     stream_put_board<G>(s_bits, head + lane * T::DENSE, j, black.w[j], white.w[j], invd.w[j], flags);
             }
             __syncwarp();
-            if (a.obs_dtype == DT_F32) emit_f32<32>(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane);
-            else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
+            emit_obs<32>(a.obs_dtype, s_bits, s_lut, head, count, a.obs_ring, at, lane);
             __syncwarp();
         }
     }
@@ -856,6 +901,26 @@ __global__ void k_unpack(const uint32_t* rec, long long batch, T* dense) {
     dense[e] = v ? T(1) : T(0);
 }
 
+template <class G>
+__global__ void k_unpack16(const uint32_t* rec, long long batch, uint16_t one, uint16_t* dense) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * 6 * G::NP) return;
+    const long long b = e / (6 * G::NP);
+    const int rem = int(e - b * 6 * G::NP);
+    const int ch = rem / G::NP, pt = rem - ch * G::NP;
+    const uint32_t* r = rec + b * G::REC_W32;
+    bool v;
+    if (ch == 2) v = r[G::FLAGS_IDX] & FLAG_TURN;
+    else if (ch == 4) v = r[G::FLAGS_IDX] & FLAG_PASS;
+    else if (ch == 5) v = r[G::FLAGS_IDX] & FLAG_DONE;
+    else {
+        const int plane = ch == 3 ? 2 : ch;
+        const int row = pt / G::N, c = pt - row * G::N, j = row / G::RPL;
+        v = (rec_word<G>(r, plane, j) >> ((row - j * G::RPL) * G::S + c)) & 1;
+    }
+    dense[e] = v ? one : uint16_t(0);
+}
+
 template <class G, class T>
 __global__ void k_valid(const uint32_t* rec, long long batch, int ended_quirk, T* out) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -985,6 +1050,8 @@ struct Launch {
         const unsigned grid = blocks_for(batch * (3 * G::LPB + 1), 256);
         if (dtype == DT_U8) k_pack<G, uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(dense), batch, rec);
         else if (dtype == DT_F32) k_pack<G, float><<<grid, 256, 0, s>>>(static_cast<const float*>(dense), batch, rec);
+        else if (dtype == DT_BF16 || dtype == DT_F16)       // any non-zero bit pattern is a stone (0x8000 = -0 is not used)
+            k_pack<G, uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(dense), batch, rec);
         else k_pack<G, double><<<grid, 256, 0, s>>>(static_cast<const double*>(dense), batch, rec);
         return cudaGetLastError();
     }
@@ -993,6 +1060,9 @@ struct Launch {
         const unsigned grid = blocks_for(batch * 6 * G::NP, 256);
         if (dtype == DT_U8) k_unpack<G, uint8_t><<<grid, 256, 0, s>>>(rec, batch, static_cast<uint8_t*>(dense));
         else if (dtype == DT_F32) k_unpack<G, float><<<grid, 256, 0, s>>>(rec, batch, static_cast<float*>(dense));
+        else if (dtype == DT_BF16 || dtype == DT_F16)
+            k_unpack16<G><<<grid, 256, 0, s>>>(rec, batch, dtype == DT_BF16 ? uint16_t(0x3F80) : uint16_t(0x3C00),
+                                               static_cast<uint16_t*>(dense));
         else k_unpack<G, double><<<grid, 256, 0, s>>>(rec, batch, static_cast<double*>(dense));
         return cudaGetLastError();
     }

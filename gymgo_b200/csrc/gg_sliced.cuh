@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(SlicedTile<G, K>::THREADS, SlicedTile<G, K>::M
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    if (tid < 16) s_lut[tid] = make_float4(float(tid & 1), float((tid >> 1) & 1), float((tid >> 2) & 1), float((tid >> 3) & 1));
+    obs_lut_init(s_lut, a.obs_dtype, tid);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(SlicedTile<G, K>::THREADS, SlicedTile<G, K>::M
     int nbw = nb - warp * S::BPW;
     nbw = nbw < 0 ? 0 : (nbw > S::BPW ? S::BPW : nbw);
     const long long e0 = wb0 * T::DENSE;
-    const int align_mask = a.obs_dtype == DT_F32 ? 3 : 15;
+    const int align_mask = obs_align_mask(a.obs_dtype);
     const int count = nbw * T::DENSE;
     const long long slot_elems = a.boards * T::DENSE;
     const unsigned long long gb = a.board0 + (unsigned long long)slot;
@@ -333,8 +333,7 @@ __global__ void __launch_bounds__(SlicedTile<G, K>::THREADS, SlicedTile<G, K>::M
                 }
             }
             __syncwarp();
-            if (a.obs_dtype == DT_F32) emit_f32<32>(s_bits, s_lut, head, count, static_cast<float*>(a.obs_ring) + at, lane);
-            else emit_u8(s_bits, head, count, static_cast<uint8_t*>(a.obs_ring) + at, lane, 32);
+            emit_obs<32>(a.obs_dtype, s_bits, s_lut, head, count, a.obs_ring, at, lane);
             __syncwarp();
         }
     }

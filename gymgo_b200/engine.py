@@ -10,7 +10,8 @@ import torch
 
 from . import _cabi
 
-_TORCH2GG = {torch.uint8: _cabi.GG_U8, torch.float32: _cabi.GG_F32, torch.float64: _cabi.GG_F64}
+_TORCH2GG = {torch.uint8: _cabi.GG_U8, torch.float32: _cabi.GG_F32, torch.float64: _cabi.GG_F64,
+             torch.bfloat16: _cabi.GG_BF16, torch.float16: _cabi.GG_F16}
 _tls = threading.local()
 
 

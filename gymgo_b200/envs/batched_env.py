@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from .. import _cabi
-from ..engine import GoEngine
+from ..engine import _TORCH2GG, GoEngine
 
 _REWARD = {"real": _cabi.GG_REWARD_REAL, "heuristic": _cabi.GG_REWARD_HEURISTIC}
 
@@ -66,7 +66,7 @@ class BatchedGoEnv(object):
                 (self.rec.data_ptr(), self.batch_size, self.size, self.done.data_ptr()),
                 (self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(), self.status.data_ptr(),
                  self.batch_size, self.size, _cabi.GG_STEP_REFUSE_DONE, self.obs.data_ptr(),
-                 _cabi.GG_U8 if self.obs_dtype == torch.uint8 else _cabi.GG_F32, self.done.data_ptr(), None,
+                 _TORCH2GG[self.obs_dtype], self.done.data_ptr(), None,
                  self.reward.data_ptr(), self.reward_mode, float(self.komi)))
         reset_args, step_args = self._c_args
         if auto_reset:

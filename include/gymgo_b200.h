@@ -59,6 +59,8 @@ extern "C" {
 #define GG_U8 0
 #define GG_F32 1
 #define GG_F64 2 /* pack/unpack/valid_moves only (the reference's own dtype) */
+#define GG_BF16 3 /* bfloat16 0/1 (0x3F80): observations, pack/unpack - feeds bf16 networks without a cast */
+#define GG_F16 4  /* float16 0/1 (0x3C00): observations, pack/unpack */
 
 /* reward_mode of gg_step / gg_rollout_step (GoEnv.reward, go_env.py:128-149) */
 #define GG_REWARD_NONE 0
@@ -103,7 +105,7 @@ GG_API int gg_reset(void *rec, int64_t batch, int n, const uint8_t *mask, void *
  *   actions          int32 [B], N*N = pass
  *   status           uint8 [B] or NULL
  *   flags            GG_STEP_* bits
- *   obs_out          NULL, or dense [B,6,N,N] of obs_dtype (GG_U8 or GG_F32) receiving the new state -
+ *   obs_out          NULL, or dense [B,6,N,N] of obs_dtype (GG_U8, GG_F32, GG_BF16 or GG_F16) receiving the new state -
  *                    what GoEnv.step returns as the observation (go_env.py:64)
  *   done_out         NULL, or uint8 [B]: game over after this ply (gogame.game_ended, gogame.py:208-214)
  *   areas_out        NULL, or int32 [B,2] Tromp-Taylor (black, white) areas of the new state

@@ -96,7 +96,7 @@ def test_golden_soup(eng, n):
 
 @pytest.mark.parametrize("n", (3, 7, 9, 19))
 @pytest.mark.parametrize("batch", (1, 7, 39, 41, 130, 1000))
-@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8))
+@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.bfloat16, torch.float16))
 def test_obs_emission_tail_tiles(eng, n, batch, dtype):
     """the fused dense output equals the independent unpack kernel for ragged batch sizes"""
     e = eng(n)
@@ -106,8 +106,10 @@ def test_obs_emission_tail_tiles(eng, n, batch, dtype):
     acts = e.sample_legal(rec, 3, 0, 0)
     guard = torch.full((batch + 1, 6, n, n), 7, dtype=dtype, device="cuda")      # one extra board as canary
     res = e.step(rec, acts, obs=guard[:batch])
-    assert np.array_equal(res["obs"].cpu().numpy(), e.unpack(res["rec"], dtype=dtype).cpu().numpy())
+    assert torch.equal(res["obs"], e.unpack(res["rec"], dtype=dtype))
+    assert torch.equal(res["obs"].float(), e.unpack(res["rec"], dtype=torch.float32))
     assert bool((guard[batch] == 7).all())                                          # nothing written past the end
+    assert torch.equal(e.pack(res["obs"]), res["rec"])                              # and it packs back to the record
 
 
 @pytest.mark.parametrize("n,boards,steps", ((5, 333, 120), (9, 1000, 260), (13, 200, 200), (19, 150, 300)))
@@ -142,7 +144,7 @@ def test_rollout_vs_oracle_replay(eng, n, boards, steps):
 
 
 @pytest.mark.parametrize("n,boards", ((9, 1003), (19, 149), (7, 333), (5, 77), (17, 41), (13, 64)))
-@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8))
+@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.bfloat16))
 def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
     """gg_rollout (boards resident in registers for several plies, per-warp observation emission incl. ragged
     tiles and unaligned warp slices) reproduces the ply-by-ply kernel bit for bit: records, observations of every
@@ -178,7 +180,7 @@ def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
 
 
 @pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 141), (13, 97), (16, 33)))
-@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8))
+@pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.float16))
 def test_thread_per_board_variant_matches(eng, n, boards, dtype, monkeypatch):
     """the thread-per-board rollout kernel is bit-identical to the lane-sliced one (GG_ROLLOUT_VARIANT forces either)"""
     e = eng(n)
