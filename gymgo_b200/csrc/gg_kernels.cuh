@@ -275,24 +275,28 @@ __device__ __forceinline__ void emit_f32(const uint32_t* s_bits, const float4* s
             base[e] = ((s_bits[e >> 5] >> (e & 31)) & 1u) ? 1.0f : 0.0f;
     }
 }
-__device__ __forceinline__ void emit_u8(const uint32_t* s_bits, int head, int count, uint8_t* base, int tid, int nthreads) {
+// u8: 16 elements per 16-byte vector; each of the two stream bytes -> 8 output bytes through a 256-entry table.
+template <int NT>
+__device__ __forceinline__ void emit_u8(const uint32_t* s_bits, const uint2* s_lut, int head, int count, uint8_t* base, int tid) {
+    static_assert(NT % 32 == 0, "stride must keep the half-word position fixed per thread");
     const int end = head + count;
-    const int nq = (end + 15) >> 4;
+    const int q_lo = (head + 15) >> 4, q_hi = end >> 4;             // full vectors are [q_lo, q_hi)
     uint4* base4 = reinterpret_cast<uint4*>(base);
-    for (int q = tid; q < nq; q += nthreads) {
-        const uint32_t h = (s_bits[q >> 1] >> ((q & 1) << 4)) & 0xffffu;
-        const int e = q << 4;
-        if (e >= head && e + 16 <= end) {
-            uint4 v;
-            v.x = ((h & 15u) * 0x00204081u) & 0x01010101u;          // 4 bits -> 4 bytes of 0/1
-            v.y = (((h >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            v.z = (((h >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-            v.w = (((h >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-            __stcs(base4 + q, v);
-        } else {
-            for (int i = 0; i < 16; ++i)
-                if (e + i >= head && e + i < end) base[e + i] = uint8_t((h >> i) & 1u);
-        }
+    const int sh = (tid & 1) << 4;
+    int q = tid;
+    if (q < q_lo) q += NT;
+    const uint32_t* w = s_bits + (q >> 1);
+    uint4* g = base4 + q;
+#pragma unroll 4
+    for (; q < q_hi; q += NT, w += NT / 2, g += NT) {
+        const uint32_t h = *w >> sh;
+        const uint2 lo = s_lut[h & 255u], hi = s_lut[(h >> 8) & 255u];
+        __stcs(g, make_uint4(lo.x, lo.y, hi.x, hi.y));
+    }
+    if (tid < 32) {                                                  // the (at most two) partial vectors
+        const int e = tid < 16 ? tid : (q_hi << 4) + tid - 16;
+        if (e >= head && e < end && (e < (q_lo << 4) || e >= (q_hi << 4)))
+            base[e] = uint8_t((s_bits[e >> 5] >> (e & 31)) & 1u);
     }
 }
 
@@ -322,10 +326,19 @@ __device__ __forceinline__ void emit_h16(const uint32_t* s_bits, const uint2* s_
     }
 }
 
-// dtype dispatch shared by every kernel that writes observations
+// dtype dispatch shared by every kernel that writes observations.  One shared-memory table serves all dtypes:
+// f32: 16 x float4 (nibble -> 4 floats); bf16/f16: 16 x uint2 (nibble -> 4 halves); u8: 256 x uint2 (byte -> 8 bytes).
+constexpr int LUT_F4 = 128;                                          // 2 KB
 __device__ __forceinline__ uint16_t obs_one16(int dt) { return dt == DT_BF16 ? uint16_t(0x3F80) : uint16_t(0x3C00); }
 __device__ __forceinline__ int obs_align_mask(int dt) { return dt == DT_F32 ? 3 : (dt == DT_U8 ? 15 : 7); }
+template <int NT>
 __device__ __forceinline__ void obs_lut_init(float4* s_lut, int dt, int tid) {
+    if (dt == DT_U8) {
+        for (int i = tid; i < 256; i += NT)
+            reinterpret_cast<uint2*>(s_lut)[i] = make_uint2(((i & 15u) * 0x00204081u) & 0x01010101u,   // 4 bits -> 4 bytes
+                                                             (((i >> 4) & 15u) * 0x00204081u) & 0x01010101u);
+        return;
+    }
     if (tid >= 16) return;
     if (dt == DT_BF16 || dt == DT_F16) {
         const uint32_t one = obs_one16(dt);
@@ -340,7 +353,7 @@ template <int NT>
 __device__ __forceinline__ void emit_obs(int dt, const uint32_t* s_bits, const float4* s_lut, int head, int count, void* buf,
                                          long long at, int tid) {
     if (dt == DT_F32) emit_f32<NT>(s_bits, s_lut, head, count, static_cast<float*>(buf) + at, tid);
-    else if (dt == DT_U8) emit_u8(s_bits, head, count, static_cast<uint8_t*>(buf) + at, tid, NT);
+    else if (dt == DT_U8) emit_u8<NT>(s_bits, reinterpret_cast<const uint2*>(s_lut), head, count, static_cast<uint8_t*>(buf) + at, tid);
     else emit_h16<NT>(s_bits, reinterpret_cast<const uint2*>(s_lut), head, count, static_cast<uint16_t*>(buf) + at, tid,
                       obs_one16(dt));
 }
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     typedef Tile<G> T;
     __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
     __shared__ uint32_t s_bits[T::STREAM_W32];
-    __shared__ __align__(16) float4 s_lut[16];
+    __shared__ __align__(16) float4 s_lut[LUT_F4];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS) k_step(const StepArgs a) {
     }
     if (want_obs) {
         for (int i = tid; i < T::STREAM_W32; i += T::THREADS) s_bits[i] = 0;
-        obs_lut_init(s_lut, a.obs_dtype, tid);
+        obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
     }
     __syncthreads();
     if (MODE != MODE_CHILDREN) {
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     typedef WarpStream<G> WS;
     __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
     __shared__ uint32_t s_bits_all[T::WPC][WS::W32];
-    __shared__ __align__(16) float4 s_lut[16];
+    __shared__ __align__(16) float4 s_lut[LUT_F4];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -561,7 +574,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    obs_lut_init(s_lut, a.obs_dtype, tid);
+    obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
@@ -680,7 +693,7 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
     typedef ArrayPlane<G> P;
     __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
     __shared__ uint32_t s_bits_all[T::THREADS / 32][T::WSTREAM_W32];
-    __shared__ __align__(16) float4 s_lut[16];
+    __shared__ __align__(16) float4 s_lut[LUT_F4];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -694,7 +707,7 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    obs_lut_init(s_lut, a.obs_dtype, tid);
+    obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);

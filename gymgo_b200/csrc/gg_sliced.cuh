@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(SlicedTile<G, K>::THREADS, SlicedTile<G, K>::M
     typedef SlicedPlane<G, K> P;
     __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
     __shared__ uint32_t s_bits_all[T::WARPS][T::WSTREAM_W32];
-    __shared__ __align__(16) float4 s_lut[16];
+    __shared__ __align__(16) float4 s_lut[LUT_F4];
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(SlicedTile<G, K>::THREADS, SlicedTile<G, K>::M
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
-    obs_lut_init(s_lut, a.obs_dtype, tid);
+    obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
