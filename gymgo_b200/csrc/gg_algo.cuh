@@ -303,13 +303,17 @@ struct Algo {
         const bool gap = o.any_board(o.andnot(nb, opp));
         const bool hemmed = placed && !gap;
         P ko = o.zero();
-        const P seeds = nb & opp;
+        // Captures.  A dead group consists only of "enclosed" stones (no empty neighbour of their own), so only the
+        // enclosed stones next to the move are flooded, and only through enclosed stones: in open positions this is
+        // empty or tiny.  Such a component is alive iff it touches an opponent stone that is not enclosed.
+        const P empty_now = o.andnot(o.full(), own | opp);
+        const P enclosed = o.andnot(opp, nbrs(o, empty_now));
+        const P seeds = nb & enclosed;
         if (o.any(seeds)) {
-            const P empty = o.andnot(o.full(), own | opp);
             GG_STAT_TAG(0)
-            const P grp = flood(o, seeds, opp);                    // every opponent group touching the move
+            const P grp = flood(o, seeds, enclosed);               // enclosed components touching the move
             GG_STAT_TAG(1)
-            const P alive = flood(o, grp & nbrs(o, empty), grp);   // ... that still has a liberty
+            const P alive = flood(o, grp & nbrs(o, o.andnot(opp, enclosed)), grp);
             const P dead = o.andnot(grp, alive);
             opp = o.andnot(opp, dead);
             const int ndead = o.count2(dead);
