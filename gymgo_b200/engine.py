@@ -12,6 +12,7 @@ from . import _cabi
 
 _TORCH2GG = {torch.uint8: _cabi.GG_U8, torch.float32: _cabi.GG_F32, torch.float64: _cabi.GG_F64,
              torch.bfloat16: _cabi.GG_BF16, torch.float16: _cabi.GG_F16}
+_OBS_DTYPES = (torch.float32, torch.uint8, torch.bfloat16, torch.float16)
 _tls = threading.local()
 
 
@@ -73,6 +74,17 @@ class GoEngine(object):
             raise ValueError("actions must have shape [%d]" % batch)
         return a
 
+    def _check_out(self, t, name, shape, dtypes):
+        """optional output tensor: right device, contiguous, exact shape, allowed dtype (the C ABI trusts pointers)"""
+        if t is None:
+            return
+        if not isinstance(dtypes, (tuple, list)):
+            dtypes = (dtypes,)
+        if t.device != self.device or not t.is_contiguous() or tuple(t.shape) != tuple(shape) or t.dtype not in dtypes:
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s (got %s %s on %s)"
+                             % (name, "/".join(str(d) for d in dtypes), tuple(shape), self.device, t.dtype,
+                                tuple(t.shape), t.device))
+
     def empty(self, *shape, dtype=torch.uint8):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
@@ -124,6 +136,7 @@ class GoEngine(object):
             self._check_rec(out)
         if obs is None and obs_dtype is not None:
             obs = self.empty((b, 6, self.size, self.size), dtype=obs_dtype)
+        self._check_out(obs, "obs", (b, 6, self.size, self.size), _OBS_DTYPES)
         status = self.empty((b,)) if want_status else None
         done = self.empty((b,)) if want_done else None
         areas = self.empty((b, 2), dtype=torch.int32) if want_areas else None
@@ -139,6 +152,13 @@ class GoEngine(object):
                      reward_mode=0, komi=0.0):
         """Fused auto-reset + uniform-random-legal action + ply, in place on `rec`.  All outputs are optional
         preallocated tensors (nothing is allocated here: this is the benchmark loop)."""
+        self._check_rec(rec)
+        b = rec.shape[0]
+        self._check_out(actions, "actions", (b,), torch.int32)
+        self._check_out(obs, "obs", (b, 6, self.size, self.size), _OBS_DTYPES)
+        self._check_out(done, "done", (b,), torch.uint8)
+        self._check_out(areas, "areas", (b, 2), torch.int32)
+        self._check_out(reward, "reward", (b,), torch.float32)
         s = self._enter()
         _cabi.check(self.lib.gg_rollout_step(_ptr(rec), rec.shape[0], self.size, int(seed), int(board0), int(t),
                                              _ptr(actions), _ptr(obs), _TORCH2GG[obs.dtype] if obs is not None else 0,
@@ -148,7 +168,17 @@ class GoEngine(object):
                 done_log=None, reward_log=None, reward_mode=0, komi=0.0):
         """`steps` fused rollout plies by the persistent kernel (gg_rollout), `plies_per_launch` plies per launch.
         obs_ring: [R,B,6,N,N] ring of observation slots (ply t writes slot t % R); actions_log int32 [steps,B],
-        done_log uint8 [steps,B], reward_log float32 [steps,B] - all optional, preallocated."""
+        done_log uint8 [steps,B], reward_log float32 [steps,B] - all optional, preallocated (logs may be longer
+        than `steps`: only the first `steps` rows are written)."""
+        self._check_rec(rec)
+        b, steps = rec.shape[0], int(steps)
+        for t, name, dt in ((actions_log, "actions_log", torch.int32), (done_log, "done_log", torch.uint8),
+                            (reward_log, "reward_log", torch.float32)):
+            if t is not None and (t.dim() != 2 or t.shape[0] < steps):
+                raise ValueError("%s needs at least %d rows" % (name, steps))
+            self._check_out(t, name, (t.shape[0], b) if t is not None else None, dt)
+        if obs_ring is not None:
+            self._check_out(obs_ring, "obs_ring", (obs_ring.shape[0], b, 6, self.size, self.size), _OBS_DTYPES)
         s = self._enter()
         ring = 0 if obs_ring is None else int(obs_ring.shape[0])
         _cabi.check(self.lib.gg_rollout(_ptr(rec), rec.shape[0], self.size, int(seed), int(board0), int(t0), int(steps),

@@ -1,0 +1,37 @@
+"""CPU checks of bench.py's bookkeeping (no GPU work): algorithmic byte counts of SURVEY.md 8(d), the measured-peak
+lookup, the profiled-traffic lookup, core counting and the reference arm's JSON contract on a tiny sample."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_algorithmic_bytes_match_survey():
+    assert bench.algorithmic_bytes_per_ply(9, 4) == 2028
+    assert bench.algorithmic_bytes_per_ply(19, 4) == 8964
+    assert bench.algorithmic_bytes_per_ply(9, 1) == 570
+    assert bench.algorithmic_bytes_per_ply(19, 1) == 2466
+    assert bench.algorithmic_bytes_per_ply(9, 0) == 84 and bench.algorithmic_bytes_per_ply(19, 0) == 300
+
+
+def test_peak_and_traffic_lookups():
+    peak, src = bench.measured_peak_gbs()
+    assert 3000 < peak < 9000 and ("measured" in src or "fallback" in src)
+    t = bench.profiled_traffic("9x9", "f32", 32)
+    assert t is None or 3e9 < t < 5e9
+    assert bench.profiled_traffic("9x9", "f32", 7) is None
+    assert 1 <= bench.usable_cores() <= (os.cpu_count() or 1)
+
+
+def test_reference_arm_json_contract():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "6", "--warmup", "3"],
+                       stdout=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+    assert line["steps"] == 6 and line["warmup"] == 3
