@@ -154,7 +154,7 @@ GG_API int gg_valid_moves(const void *rec, int64_t batch, int n, int ended_quirk
  * otherwise (padded=True of gogame.children, gogame.py:175-186).
  *   child_rec   NULL or packed [B, A] records          valid   NULL or uint8 [B, A]
  *   child_obs   NULL or dense [B, A, 6, N, N]           status  NULL or uint8 [B]: 1 if a "valid" action was
- *               of obs_dtype (GG_U8/GG_F32)                     refused (finished parent with stones: the
+ *               of obs_dtype (U8/F32/BF16/F16)                  refused (finished parent with stones: the
  *                                                               reference asserts there, gogame.py:117)
  *   flags       GG_STEP_CANONICAL or 0 */
 GG_API int gg_children(const void *rec, int64_t batch, int n, uint32_t flags, void *child_rec, void *child_obs,
