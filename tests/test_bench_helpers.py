@@ -35,3 +35,11 @@ def test_reference_arm_json_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
     assert line["steps"] == 6 and line["warmup"] == 3
+
+
+def test_developer_tools_parse():
+    import ast
+    tools = os.path.join(ROOT, "tools")
+    for name in sorted(os.listdir(tools)):
+        if name.endswith(".py"):
+            ast.parse(open(os.path.join(tools, name)).read(), filename=name)

@@ -236,3 +236,28 @@ def test_batched_env_cuda_graph_step_equals_eager():
         assert torch.equal(oe, og_) and torch.equal(re_, rg) and torch.equal(de, dg)
         assert torch.equal(ie["status"], ig["status"])
     assert torch.equal(eager.rec, graph.rec) and bool(eager.done.any())
+
+
+@pytest.mark.parametrize("n,method,komi", ((5, "real", 0), (9, "heuristic", 2.5), (6, "real", 0.5), (19, "heuristic", 0)))
+def test_goenv_random_games_against_env_oracle(n, method, komi):
+    """whole random games through the drop-in GoEnv next to the oracle's restatement of the reference wrapper:
+    states, rewards, done flags, info dict, valid moves, winning()"""
+    from gymgo_b200.envs import GoEnv
+    rng = np.random.RandomState(n)
+    env, ref = GoEnv(n, komi=komi, reward_method=method), og.EnvOracle(n, komi=komi, reward_method=method)
+    plies = 0
+    for game in range(2 if n < 19 else 1):
+        assert np.array_equal(env.reset(), ref.reset())
+        done = False
+        while not done and plies < (400 if n < 19 else 260):
+            vm = env.valid_moves()
+            assert np.array_equal(vm, ref.valid_moves())
+            a = int(rng.choice(np.flatnonzero(vm)))
+            s1, r1, d1, i1 = env.step(a)
+            s2, r2, d2, i2 = ref.step(a)
+            assert np.array_equal(s1, s2) and float(r1) == float(r2) and d1 == d2
+            assert i1["turn"] == i2["turn"] and bool(i1["prev_player_passed"]) == bool(i2["prev_player_passed"])
+            assert np.array_equal(i1["invalid_moves"], i2["invalid_moves"])
+            done = bool(d1)
+            plies += 1
+        assert float(env.winning()) == float(ref.winning())
