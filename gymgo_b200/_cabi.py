@@ -13,13 +13,15 @@ _LIB = None
 GG_OK, GG_EINVAL, GG_ESIZE, GG_EALIGN, GG_ECUDA = 0, -1, -2, -3, -4
 GG_ST_OK, GG_ST_INVALID_MOVE, GG_ST_OUT_OF_RANGE, GG_ST_GAME_OVER = 0, 1, 2, 3
 GG_U8, GG_F32, GG_F64, GG_BF16, GG_F16 = 0, 1, 2, 3, 4
-GG_STEP_CANONICAL, GG_STEP_REFUSE_DONE = 1, 2
+GG_STEP_CANONICAL, GG_STEP_REFUSE_DONE, GG_STEP_AUTO_RESET, GG_STEP_RESET_SKIPS_ACTION = 1, 2, 4, 8
+GG_KERNEL_AUTO, GG_KERNEL_LANES, GG_KERNEL_THREAD, GG_KERNEL_LANES_WS = -1, 0, 1, 2
+GG_VERSION = 200
 
 GG_REWARD_NONE, GG_REWARD_REAL, GG_REWARD_HEURISTIC = 0, 1, 2
 
 EXPORTS = ("gg_version", "gg_last_cuda_error", "gg_supported", "gg_set_device", "gg_layout", "gg_pack", "gg_unpack", "gg_reset",
-           "gg_step", "gg_rollout_step", "gg_rollout", "gg_rollout_kernel", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
-           "gg_canonical", "gg_symmetry")
+           "gg_step", "gg_rollout_step", "gg_rollout", "gg_rollout_with", "gg_rollout_kernel", "gg_kernel_name", "gg_update_pieces", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
+           "gg_canonical", "gg_symmetry", "gg_host_unpack")
 
 _ERR = {GG_EINVAL: "GG_EINVAL (bad argument)", GG_ESIZE: "GG_ESIZE (board size not supported, build has 2..19)",
         GG_EALIGN: "GG_EALIGN (buffer not 16-byte aligned)", GG_ECUDA: "GG_ECUDA"}
@@ -41,7 +43,20 @@ def lib():
     path = _build.LIB
     if not os.path.exists(path):
         path = _build.build()           # raises if nvcc is missing / compilation fails
+    elif not _build.up_to_date():
+        # the sources under csrc/ changed after the library was built: rebuild where a compiler exists (a no-op
+        # otherwise would silently run stale kernels); on a box without nvcc fall through to the version check
+        try:
+            _build.nvcc()
+        except RuntimeError:
+            pass
+        else:
+            path = _build.build()
     L = ctypes.CDLL(path)
+    L.gg_version.restype = ctypes.c_int
+    if L.gg_version() != GG_VERSION:
+        raise GymGoB200Error("%s is ABI version %d, this binding needs %d: run `python -m gymgo_b200.build --force`"
+                             % (path, L.gg_version(), GG_VERSION))
     vp, i64, u64, i32, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
     ip = ctypes.POINTER(ctypes.c_int)
     L.gg_version.restype = i32
@@ -56,14 +71,19 @@ def lib():
     L.gg_step.argtypes = [vp, vp, vp, vp, i64, i32, u32, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout_step.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout.argtypes = [vp, i64, i32, u64, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp, i32, f32, vp]
+    L.gg_rollout_with.argtypes = [i32] + L.gg_rollout.argtypes
     L.gg_rollout_kernel.argtypes = [i32, i64]
     L.gg_rollout_kernel.restype = ctypes.c_char_p
+    L.gg_kernel_name.argtypes = [i32]
+    L.gg_kernel_name.restype = ctypes.c_char_p
+    L.gg_update_pieces.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     L.gg_sample_legal.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp]
     L.gg_valid_moves.argtypes = [vp, i64, i32, i32, i32, vp, vp]
     L.gg_children.argtypes = [vp, i64, i32, u32, vp, vp, i32, vp, vp, vp]
     L.gg_areas.argtypes = [vp, i64, i32, vp, vp]
     L.gg_canonical.argtypes = [vp, vp, i64, i32, vp]
     L.gg_symmetry.argtypes = [vp, vp, i64, i32, i32, vp]
+    L.gg_host_unpack.argtypes = [vp, i64, i32, i32, vp, i32]
     for name in EXPORTS:
         getattr(L, name)                # fail early if a symbol is missing
     _LIB = L

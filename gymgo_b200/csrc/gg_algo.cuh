@@ -39,7 +39,7 @@ namespace gg {
 enum : uint32_t { FLAG_TURN = 1u, FLAG_PASS = 2u, FLAG_DONE = 4u };
 enum : int { ST_OK = 0, ST_INVALID_MOVE = 1, ST_OUT_OF_RANGE = 2, ST_GAME_OVER = 3 };
 // step option bits (also the `flags` argument of gg_step in include/gymgo_b200.h)
-enum : uint32_t { OPT_CANONICAL = 1u, OPT_REFUSE_DONE = 2u };
+enum : uint32_t { OPT_CANONICAL = 1u, OPT_REFUSE_DONE = 2u, OPT_AUTO_RESET = 4u, OPT_RESET_SKIPS_ACTION = 8u };
 
 constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 constexpr int default_wordbits(int n) { return n <= 9 ? 32 : 64; }
@@ -276,6 +276,25 @@ struct Algo {
         return occ | bad | ko;
     }
 
+    // Stones of `opp` that belong to groups touching a point of `touch` and have no liberty left (update_pieces,
+    // state_utils.py:159-180).  A dead group consists only of "enclosed" stones (no empty neighbour of their own), so
+    // only the enclosed stones on `touch` are flooded, and only through enclosed stones: in open positions this is
+    // empty or tiny.  Such a component is alive iff it touches an opponent stone that is not enclosed.
+    static GG_HD P captured(const O& o, P opp, P own, P touch) {
+        const P empty_now = o.andnot(o.full(), own | opp);
+        const P enclosed = o.andnot(opp, nbrs(o, empty_now));
+        const P seeds = touch & enclosed;
+        P dead = o.zero();
+        if (o.any(seeds)) {
+            GG_STAT_TAG(0)
+            const P grp = flood(o, seeds, enclosed);               // enclosed components touching the move
+            GG_STAT_TAG(1)
+            const P alive = flood(o, grp & nbrs(o, o.andnot(opp, enclosed)), grp);
+            dead = o.andnot(grp, alive);
+        }
+        return dead;
+    }
+
     // One ply.  Planes and flags are updated in place when the returned status is ST_OK and left
     // untouched otherwise.  `action` in [0, N*N] (N*N = pass).
     template <class G>
@@ -302,22 +321,13 @@ struct Algo {
         const bool placed = o.any_board(m);
         const bool gap = o.any_board(o.andnot(nb, opp));
         const bool hemmed = placed && !gap;
+        // captures (state_utils.py:159-180), then the ko point: one group of one stone died and the move is hemmed in
+        const P dead = captured(o, opp, own, nb);
         P ko = o.zero();
-        // Captures.  A dead group consists only of "enclosed" stones (no empty neighbour of their own), so only the
-        // enclosed stones next to the move are flooded, and only through enclosed stones: in open positions this is
-        // empty or tiny.  Such a component is alive iff it touches an opponent stone that is not enclosed.
-        const P empty_now = o.andnot(o.full(), own | opp);
-        const P enclosed = o.andnot(opp, nbrs(o, empty_now));
-        const P seeds = nb & enclosed;
-        if (o.any(seeds)) {
-            GG_STAT_TAG(0)
-            const P grp = flood(o, seeds, enclosed);               // enclosed components touching the move
-            GG_STAT_TAG(1)
-            const P alive = flood(o, grp & nbrs(o, o.andnot(opp, enclosed)), grp);
-            const P dead = o.andnot(grp, alive);
+        if (o.any(dead)) {                                                 // uniform over the boards that share a vote
             opp = o.andnot(opp, dead);
             const int ndead = o.count2(dead);
-            ko = o.pick(hemmed && ndead == 1, dead, o.zero());            // one group of one stone
+            ko = o.pick(hemmed && ndead == 1, dead, o.zero());
         }
         // mask for the player who moves next (= opp colour), also recomputed on a pass (ko expires)
         const P new_invd = invalid_mask(o, opp, own, ko);

@@ -1,8 +1,10 @@
 // gg_api.cu - the C ABI of include/gymgo_b200.h: argument checks + dispatch on the board size.
 // No allocation, no synchronisation, no global state besides the last-error string.
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
+
+#include <thread>
+#include <vector>
 
 #include "../../include/gymgo_b200.h"
 #include "gg_kernels.cuh"
@@ -26,16 +28,19 @@ static const SizeVTable* lookup(int n) {
 
 static thread_local char g_err[256] = "";
 
-// Which persistent rollout kernel serves (n, batch).  Measured (profiles/r01_variant_threshold.json, f32
-// observations): both kernels sit within a few percent of the pure-write floor; thread-per-board is ahead by up
-// to 5 % on small boards around 64 Ki boards (the lane-sliced kernel cannot fully overlap rules and stores there),
-// behind below 32 Ki (too few warps) and level or slightly behind at 128 Ki (both write-bound).
-// GG_ROLLOUT_VARIANT=0/1/2 overrides the choice for A/B measurements.
-static int rollout_variant(const SizeVTable* v, int64_t batch) {
-    const char* forced = getenv("GG_ROLLOUT_VARIANT");
-    if (forced) return atoi(forced);
+// Which persistent rollout kernel serves (n, batch) when the caller asks for GG_KERNEL_AUTO.  Measured on the B200
+// with f32 observations (profiles/r01_variant_threshold.json, profiles/r02_kernel_ab.json): all kernels sit within a
+// few percent of the pure-write floor on small boards; thread-per-board is ahead by up to 5 % on small boards around
+// 64 Ki boards, behind below 32 Ki (too few warps) and level at 128 Ki (write-bound either way).
+static int auto_kernel(const SizeVTable* v, int64_t batch) {
     const bool tpb_ok = v->wordbits == 32 && v->lpb <= 3;
-    return (tpb_ok && batch >= 49152 && batch < 98304) ? 1 : 0;
+    if (tpb_ok && batch >= 49152 && batch < 98304) return GG_KERNEL_THREAD;
+    return GG_KERNEL_LANES;
+}
+static const char* kernel_name(int k) {
+    return k == GG_KERNEL_THREAD ? "k_rollout_tpb (thread per board)"
+                                 : (k == GG_KERNEL_LANES_WS ? "k_rollout_ws (lane-sliced boards, emitter warps)"
+                                                            : "k_rollout (lane-sliced boards)");
 }
 
 static int finish(cudaError_t e) {
@@ -46,6 +51,52 @@ static int finish(cudaError_t e) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static bool dense_dtype_ok(int dt, bool allow_f64) {
     return dt == GG_U8 || dt == GG_F32 || dt == GG_BF16 || dt == GG_F16 || (allow_f64 && dt == GG_F64);
+}
+}  // namespace gg
+
+// ---------------------------------------------------------------------------------------------- host codec
+// Packed records in HOST memory -> dense [B,6,N,N] in host memory: for consumers that move the 40x smaller packed
+// records over PCIe (HostStepper(returns="packed")) and expand next to the CPU.  A codec, not a rules path: no Go
+// logic runs on the host.
+namespace gg {
+template <class T>
+static void host_unpack_range(const uint8_t* rec, int64_t b0, int64_t b1, int n, const SizeVTable* v, T one, T* dense) {
+    const int np = n * n, s = n + 1, word_bytes = v->wordbits / 8, plane_bytes = v->lpb * word_bytes;
+    for (int64_t b = b0; b < b1; ++b) {
+        const uint8_t* r = rec + b * v->rec_bytes;
+        T* out = dense + b * 6 * np;
+        uint32_t flags;
+        memcpy(&flags, r + 3 * plane_bytes, 4);
+        const int chan_of_plane[3] = {0, 1, 3};
+        for (int p = 0; p < 3; ++p) {
+            T* o = out + chan_of_plane[p] * np;
+            for (int row = 0; row < n; ++row) {
+                const int j = row / v->rpl;
+                uint64_t w = 0;
+                memcpy(&w, r + p * plane_bytes + j * word_bytes, word_bytes);
+                const uint64_t bits = w >> ((row - j * v->rpl) * s);
+                for (int c = 0; c < n; ++c) o[row * n + c] = ((bits >> c) & 1) ? one : T(0);
+            }
+        }
+        const T turn = (flags & FLAG_TURN) ? one : T(0), pass = (flags & FLAG_PASS) ? one : T(0), done = (flags & FLAG_DONE) ? one : T(0);
+        for (int i = 0; i < np; ++i) {
+            out[2 * np + i] = turn;
+            out[4 * np + i] = pass;
+            out[5 * np + i] = done;
+        }
+    }
+}
+template <class T>
+static void host_unpack(const uint8_t* rec, int64_t batch, int n, const SizeVTable* v, T one, T* dense, int threads) {
+    if (threads <= 1 || batch < 4096) return host_unpack_range<T>(rec, 0, batch, n, v, one, dense);
+    std::vector<std::thread> pool;
+    const int64_t per = (batch + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        const int64_t b0 = t * per, b1 = b0 + per < batch ? b0 + per : batch;
+        if (b0 >= b1) break;
+        pool.emplace_back([=] { host_unpack_range<T>(rec, b0, b1, n, v, one, dense); });
+    }
+    for (auto& th : pool) th.join();
 }
 }  // namespace gg
 
@@ -97,7 +148,7 @@ GG_API int gg_step(const void* rec_in, const int32_t* actions, void* rec_out, ui
             int reward_mode, float komi, void* stream) {
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
-    if (batch < 0 || (flags & ~(GG_STEP_CANONICAL | GG_STEP_REFUSE_DONE))) return GG_EINVAL;
+    if (batch < 0 || (flags & ~(GG_STEP_CANONICAL | GG_STEP_REFUSE_DONE | GG_STEP_AUTO_RESET | GG_STEP_RESET_SKIPS_ACTION))) return GG_EINVAL;
     if (batch > 0 && (!rec_in || !rec_out || !actions)) return GG_EINVAL;
     if (obs_out && !dense_dtype_ok(obs_dtype, false)) return GG_EINVAL;
     if (reward_mode < GG_REWARD_NONE || reward_mode > GG_REWARD_HEURISTIC) return GG_EINVAL;
@@ -148,12 +199,13 @@ GG_API int gg_rollout_step(void* rec, int64_t batch, int n, uint64_t seed, uint6
     return finish(v->step(a, MODE_ROLLOUT, static_cast<cudaStream_t>(stream)));
 }
 
-GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
-               int plies_per_launch, int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring,
-               uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* stream) {
+GG_API int gg_rollout_with(int kernel, void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
+                    int plies_per_launch, int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring,
+                    uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* stream) {
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
     if (batch < 0 || steps < 0 || plies_per_launch < 1 || (batch > 0 && !rec)) return GG_EINVAL;
+    if (kernel < GG_KERNEL_AUTO || kernel > GG_KERNEL_LANES_WS) return GG_EINVAL;
     if (obs_ring_buf && (!dense_dtype_ok(obs_dtype, false) || obs_ring < 1)) return GG_EINVAL;
     if (reward_mode < GG_REWARD_NONE || reward_mode > GG_REWARD_HEURISTIC) return GG_EINVAL;
     if (!aligned16(rec) || !aligned16(obs_ring_buf)) return GG_EALIGN;
@@ -168,10 +220,7 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
     a.obs_ring = obs_ring_buf;
     a.obs_dtype = obs_dtype;
     a.ring = obs_ring_buf ? obs_ring : 1;
-    // developer switch (A/B measurements only): GG_ROLLOUT_VARIANT=1 selects the thread-per-board kernel on small boards
-    a.variant = rollout_variant(v, batch);
-    const char* slice_k = getenv("GG_ROLLOUT_K");
-    a.slice_k = slice_k ? atoi(slice_k) : 2;
+    a.variant = kernel == GG_KERNEL_AUTO ? auto_kernel(v, batch) : kernel;
     for (int p = 0; p < steps; p += plies_per_launch) {
         a.t0 = t0 + uint64_t(p);
         a.plies = steps - p < plies_per_launch ? steps - p : plies_per_launch;
@@ -184,12 +233,45 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
     return GG_OK;
 }
 
+GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
+               int plies_per_launch, int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring,
+               uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* stream) {
+    return gg_rollout_with(GG_KERNEL_AUTO, rec, batch, n, seed, board0, t0, steps, plies_per_launch, actions_log, obs_ring_buf,
+                           obs_dtype, obs_ring, done_log, reward_log, reward_mode, komi, stream);
+}
+
 GG_API const char* gg_rollout_kernel(int n, int64_t batch) {
     const SizeVTable* v = lookup(n);
-    if (!v) return "";
-    const int variant = rollout_variant(v, batch);
-    return variant == 1 ? "k_rollout_tpb (thread per board)"
-                        : (variant == 2 ? "k_rollout_sliced (several words per lane)" : "k_rollout (lane-sliced boards)");
+    return v ? kernel_name(auto_kernel(v, batch)) : "";
+}
+
+GG_API const char* gg_kernel_name(int kernel) {
+    return (kernel >= GG_KERNEL_LANES && kernel <= GG_KERNEL_LANES_WS) ? kernel_name(kernel) : "";
+}
+
+GG_API int gg_update_pieces(void* rec, const void* touch, const int32_t* player, void* killed, int64_t batch, int n, void* stream) {
+    const SizeVTable* v = lookup(n);
+    if (!v) return GG_ESIZE;
+    if (batch < 0 || (batch > 0 && (!rec || !touch || !player || !killed))) return GG_EINVAL;
+    if (rec == killed || touch == killed) return GG_EINVAL;
+    if (!aligned16(rec) || !aligned16(touch) || !aligned16(killed)) return GG_EALIGN;
+    return finish(v->capture(static_cast<uint32_t*>(rec), static_cast<const uint32_t*>(touch), player,
+                             static_cast<uint32_t*>(killed), batch, static_cast<cudaStream_t>(stream)));
+}
+
+GG_API int gg_host_unpack(const void* rec_host, int64_t batch, int n, int dtype, void* dense_host, int threads) {
+    const SizeVTable* v = lookup(n);
+    if (!v) return GG_ESIZE;
+    if (batch < 0 || !dense_dtype_ok(dtype, true) || (batch > 0 && (!rec_host || !dense_host))) return GG_EINVAL;
+    if (threads <= 0) threads = int(std::thread::hardware_concurrency());
+    if (threads > 64) threads = 64;
+    const uint8_t* rec = static_cast<const uint8_t*>(rec_host);
+    if (dtype == GG_U8) host_unpack<uint8_t>(rec, batch, n, v, uint8_t(1), static_cast<uint8_t*>(dense_host), threads);
+    else if (dtype == GG_F32) host_unpack<float>(rec, batch, n, v, 1.0f, static_cast<float*>(dense_host), threads);
+    else if (dtype == GG_F64) host_unpack<double>(rec, batch, n, v, 1.0, static_cast<double*>(dense_host), threads);
+    else host_unpack<uint16_t>(rec, batch, n, v, dtype == GG_BF16 ? uint16_t(0x3F80) : uint16_t(0x3C00),
+                               static_cast<uint16_t*>(dense_host), threads);
+    return GG_OK;
 }
 
 GG_API int gg_sample_legal(const void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,

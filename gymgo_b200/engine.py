@@ -110,6 +110,7 @@ class GoEngine(object):
         self._check_rec(rec)
         if out is None:
             out = self.empty((rec.shape[0], 6, self.size, self.size), dtype=dtype)
+        self._check_out(out, "out", (rec.shape[0], 6, self.size, self.size), tuple(_TORCH2GG))
         s = self._enter()
         _cabi.check(self.lib.gg_unpack(_ptr(rec), rec.shape[0], self.size, _TORCH2GG[out.dtype], _ptr(out), s))
         return out
@@ -117,16 +118,20 @@ class GoEngine(object):
     def reset(self, rec, mask=None):
         self._check_rec(rec)
         if mask is not None:
-            mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+            mask = torch.as_tensor(mask)
+            if tuple(mask.shape) != (rec.shape[0],):
+                raise ValueError("mask must have shape [%d] (one entry per board), got %s" % (rec.shape[0], tuple(mask.shape)))
+            mask = mask.ne(0).to(device=self.device, dtype=torch.uint8).contiguous()
         s = self._enter()
         _cabi.check(self.lib.gg_reset(_ptr(rec), rec.shape[0], self.size, _ptr(mask), s))
         return rec
 
     # ------------------------------------------------------------------ the hot path
     def step(self, rec, actions, out=None, canonical=False, refuse_done=False, obs=None, obs_dtype=None,
-             want_status=True, want_done=False, want_areas=False, reward_mode=0, komi=0.0):
+             want_status=True, want_done=False, want_areas=False, reward_mode=0, komi=0.0, auto_reset=False):
         """One ply per board.  Returns dict(rec, status, obs, done, areas, reward) of device tensors
-        (entries not asked for are None).  `out=rec` steps in place."""
+        (entries not asked for are None).  `out=rec` steps in place.  auto_reset: boards whose record is finished
+        restart from the empty position before playing their action (GG_STEP_AUTO_RESET)."""
         self._check_rec(rec)
         b = rec.shape[0]
         a = self._actions(actions, b)
@@ -134,6 +139,8 @@ class GoEngine(object):
             out = torch.empty_like(rec)
         else:
             self._check_rec(out)
+            if out.shape[0] != b:
+                raise ValueError("out must hold %d records" % b)
         if obs is None and obs_dtype is not None:
             obs = self.empty((b, 6, self.size, self.size), dtype=obs_dtype)
         self._check_out(obs, "obs", (b, 6, self.size, self.size), _OBS_DTYPES)
@@ -141,7 +148,8 @@ class GoEngine(object):
         done = self.empty((b,)) if want_done else None
         areas = self.empty((b, 2), dtype=torch.int32) if want_areas else None
         reward = self.empty((b,), dtype=torch.float32) if reward_mode else None
-        flags = (_cabi.GG_STEP_CANONICAL if canonical else 0) | (_cabi.GG_STEP_REFUSE_DONE if refuse_done else 0)
+        flags = (_cabi.GG_STEP_CANONICAL if canonical else 0) | (_cabi.GG_STEP_REFUSE_DONE if refuse_done else 0) \
+            | (_cabi.GG_STEP_AUTO_RESET if auto_reset else 0)
         s = self._enter()
         _cabi.check(self.lib.gg_step(_ptr(rec), _ptr(a), _ptr(out), _ptr(status), b, self.size, flags, _ptr(obs),
                                      _TORCH2GG[obs.dtype] if obs is not None else 0, _ptr(done), _ptr(areas),
@@ -165,11 +173,12 @@ class GoEngine(object):
                                              _ptr(done), _ptr(areas), _ptr(reward), int(reward_mode), float(komi), s))
 
     def rollout(self, rec, seed, board0, t0, steps, plies_per_launch=32, actions_log=None, obs_ring=None,
-                done_log=None, reward_log=None, reward_mode=0, komi=0.0):
+                done_log=None, reward_log=None, reward_mode=0, komi=0.0, kernel=_cabi.GG_KERNEL_AUTO):
         """`steps` fused rollout plies by the persistent kernel (gg_rollout), `plies_per_launch` plies per launch.
         obs_ring: [R,B,6,N,N] ring of observation slots (ply t writes slot t % R); actions_log int32 [steps,B],
         done_log uint8 [steps,B], reward_log float32 [steps,B] - all optional, preallocated (logs may be longer
-        than `steps`: only the first `steps` rows are written)."""
+        than `steps`: only the first `steps` rows are written).  kernel: GG_KERNEL_* (AUTO = the measured choice; the
+        kernels are bit-identical, the explicit values exist for A/B measurements and parity tests)."""
         self._check_rec(rec)
         b, steps = rec.shape[0], int(steps)
         for t, name, dt in ((actions_log, "actions_log", torch.int32), (done_log, "done_log", torch.uint8),
@@ -181,10 +190,10 @@ class GoEngine(object):
             self._check_out(obs_ring, "obs_ring", (obs_ring.shape[0], b, 6, self.size, self.size), _OBS_DTYPES)
         s = self._enter()
         ring = 0 if obs_ring is None else int(obs_ring.shape[0])
-        _cabi.check(self.lib.gg_rollout(_ptr(rec), rec.shape[0], self.size, int(seed), int(board0), int(t0), int(steps),
-                                        int(plies_per_launch), _ptr(actions_log), _ptr(obs_ring),
-                                        _TORCH2GG[obs_ring.dtype] if obs_ring is not None else 0, ring, _ptr(done_log),
-                                        _ptr(reward_log), int(reward_mode), float(komi), s))
+        _cabi.check(self.lib.gg_rollout_with(int(kernel), _ptr(rec), rec.shape[0], self.size, int(seed), int(board0),
+                                             int(t0), int(steps), int(plies_per_launch), _ptr(actions_log), _ptr(obs_ring),
+                                             _TORCH2GG[obs_ring.dtype] if obs_ring is not None else 0, ring,
+                                             _ptr(done_log), _ptr(reward_log), int(reward_mode), float(komi), s))
 
     def sample_legal(self, rec, seed, board0, t):
         self._check_rec(rec)
@@ -217,6 +226,23 @@ class GoEngine(object):
                                          _ptr(valid), _ptr(status), s))
         return dict(rec=crec, obs=cobs, valid=valid, status=status)
 
+    def update_pieces(self, rec, touch, player):
+        """Capture removal alone (state_utils.update_pieces, state_utils.py:159-180), in place on `rec`: groups of colour
+        1 - player[b] touching a point of `touch` (records whose BLACK plane carries the adjacent locations) without a
+        liberty are removed.  -> records whose BLACK plane holds the removed stones."""
+        self._check_rec(rec)
+        self._check_rec(touch)
+        b = rec.shape[0]
+        if touch.shape[0] != b:
+            raise ValueError("touch must hold %d records" % b)
+        player = torch.as_tensor(player).reshape(-1).to(device=self.device, dtype=torch.int32).contiguous()
+        if player.shape != (b,):
+            raise ValueError("player must have shape [%d]" % b)
+        killed = torch.empty_like(rec)
+        s = self._enter()
+        _cabi.check(self.lib.gg_update_pieces(_ptr(rec), _ptr(touch), _ptr(player), _ptr(killed), b, self.size, s))
+        return killed
+
     def areas(self, rec):
         self._check_rec(rec)
         out = self.empty((rec.shape[0], 2), dtype=torch.int32)
@@ -228,6 +254,10 @@ class GoEngine(object):
         self._check_rec(rec)
         if out is None:
             out = torch.empty_like(rec)
+        else:
+            self._check_rec(out)
+            if out.shape[0] != rec.shape[0]:
+                raise ValueError("out must hold %d records" % rec.shape[0])
         s = self._enter()
         _cabi.check(self.lib.gg_canonical(_ptr(rec), _ptr(out), rec.shape[0], self.size, s))
         return out

@@ -5,7 +5,7 @@ state tensors, float32 like GoEnv.observation_space (go_env.py:35-36) unless ano
 import numpy as np
 import torch
 
-from .. import _cabi
+from .. import _cabi, hostmem
 from ..engine import _TORCH2GG, GoEngine
 
 _REWARD = {"real": _cabi.GG_REWARD_REAL, "heuristic": _cabi.GG_REWARD_HEURISTIC}
@@ -16,8 +16,8 @@ class BatchedGoEnv(object):
                  strict=False, seed=0, board_offset=0, use_cuda_graph=False):
         """board_offset: global index of board 0 (so that rollouts are identical however the global batch is
         sharded over GPUs); strict: raise AssertionError when any board refuses its action;
-        use_cuda_graph: step() replays a captured CUDA graph (reset + ply kernels) instead of enqueuing the
-        launches from Python - the C ABI only enqueues work on the caller's stream, so it is capturable."""
+        use_cuda_graph: step() replays a captured CUDA graph instead of enqueuing the launch from Python - the C ABI
+        only enqueues work on the caller's stream, so it is capturable."""
         if reward_method not in _REWARD:
             raise ValueError("reward_method must be 'real' or 'heuristic'")
         self.engine = GoEngine(size, device)
@@ -27,8 +27,11 @@ class BatchedGoEnv(object):
         e = self.engine
         self.rec = e.new_records(self.batch_size)
         self.obs = e.empty((self.batch_size, 6, size, size), dtype=obs_dtype)
-        self.reward = e.empty((self.batch_size,), dtype=torch.float32)
-        self.done = e.empty((self.batch_size,))
+        # reward (f32) and done (u8) live back to back in one buffer so that a host-facing loop fetches both with a
+        # single device->host copy (HostStepper below)
+        self._tail = e.empty((5 * self.batch_size,))
+        self.reward = self._tail[:4 * self.batch_size].view(torch.float32)
+        self.done = self._tail[4 * self.batch_size:]
         self.status = e.empty((self.batch_size,))
         self.actions = e.empty((self.batch_size,), dtype=torch.int32)
         self._step_actions = e.empty((self.batch_size,), dtype=torch.int32)    # static input of step() (graph-safe)
@@ -56,27 +59,29 @@ class BatchedGoEnv(object):
         return self._step_actions
 
     def _enqueue_step(self, auto_reset):
-        """enqueue (optional reset of finished boards) + one ply on torch's current stream; inputs/outputs are the
-        env's static tensors, so the argument lists are built once and the same sequence can be captured into a
-        CUDA graph"""
+        """enqueue one ply (finished boards restart first when auto_reset) on torch's current stream: ONE kernel launch
+        (GG_STEP_AUTO_RESET does the reset inside gg_step).  Inputs/outputs are the env's static tensors, so the
+        argument tuples are built once and the launch can be captured into a CUDA graph."""
         e = self.engine
         s = e._enter()
         if self._c_args is None:
-            self._c_args = (
-                (self.rec.data_ptr(), self.batch_size, self.size, self.done.data_ptr()),
-                (self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(), self.status.data_ptr(),
-                 self.batch_size, self.size, _cabi.GG_STEP_REFUSE_DONE, self.obs.data_ptr(),
-                 _TORCH2GG[self.obs_dtype], self.done.data_ptr(), None,
-                 self.reward.data_ptr(), self.reward_mode, float(self.komi)))
-        reset_args, step_args = self._c_args
-        if auto_reset:
-            _cabi.check(e.lib.gg_reset(*reset_args, s))
-        _cabi.check(e.lib.gg_step(*step_args, s))
+            def args(flags):
+                return (self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(), self.status.data_ptr(),
+                        self.batch_size, self.size, flags, self.obs.data_ptr(), _TORCH2GG[self.obs_dtype],
+                        self.done.data_ptr(), None, self.reward.data_ptr(), self.reward_mode, float(self.komi))
+            self._c_args = {False: args(_cabi.GG_STEP_REFUSE_DONE),
+                            True: args(_cabi.GG_STEP_REFUSE_DONE | _cabi.GG_STEP_AUTO_RESET),
+                            "skip": args(_cabi.GG_STEP_REFUSE_DONE | _cabi.GG_STEP_AUTO_RESET
+                                         | _cabi.GG_STEP_RESET_SKIPS_ACTION)}
+            self._gg_step = e.lib.gg_step
+        rc = self._gg_step(*self._c_args[auto_reset if auto_reset == "skip" else bool(auto_reset)], s)
+        if rc:
+            _cabi.check(rc)
 
     def _graph(self, auto_reset):
         g = self._graphs.get(auto_reset)
         if g is None:
-            # make sure both kernels are loaded before capturing (lazy module loading): run them on a scratch board
+            # make sure the kernel is loaded before capturing (lazy module loading): run it on a scratch board
             scratch = BatchedGoEnv(1, self.size, device=self.engine.device, obs_dtype=self.obs_dtype)
             scratch._step_actions.fill_(self.size * self.size)
             scratch._enqueue_step(True)
@@ -90,14 +95,16 @@ class BatchedGoEnv(object):
     def step(self, actions, auto_reset=False):
         """actions: int [B] (N*N = pass) -> (obs [B,6,N,N], reward [B] f32, done [B] u8, info).
         Finished boards refuse to step (status 3, GoEnv's `assert not self.done`) until reset;
-        auto_reset=True first resets the boards that finished on the previous step (vector-env style)."""
+        auto_reset=True first resets the boards that finished on the previous step and plays their action on the fresh
+        board; auto_reset="skip" resets them and ignores their action for this step (gymnasium next-step autoreset).
+        The returned tensors are the env's static buffers: the next step() overwrites them - clone() what you keep."""
         if actions is not self._step_actions:                       # (passing env.action_buffer skips all of this)
             a = self.engine._actions(actions, self.batch_size)
             if a.data_ptr() != self._step_actions.data_ptr():
                 self._step_actions.copy_(a, non_blocking=True)
         if self.use_cuda_graph:
             self.engine._enter()
-            self._graph(bool(auto_reset)).replay()
+            self._graph(auto_reset if auto_reset == "skip" else bool(auto_reset)).replay()
         else:
             self._enqueue_step(auto_reset)
         if self.strict and bool(self.status.any()):
@@ -105,6 +112,10 @@ class BatchedGoEnv(object):
             raise AssertionError(("refused action", int(self._step_actions[i]), "board %d" % i,
                                   "status %d" % int(self.status[i])))
         return self.obs, self.reward, self.done, {"status": self.status}
+
+    def host_stepper(self, returns="obs", auto_reset=True, use_cuda_graph=True):
+        """-> HostStepper: the step with HOST buffers (pinned actions in, pinned results out); see the class"""
+        return HostStepper(self, returns=returns, auto_reset=auto_reset, use_cuda_graph=use_cuda_graph)
 
     def random_step(self):
         """fused: auto-reset finished boards, draw a uniformly random legal action (incl. pass), play it.
@@ -154,3 +165,85 @@ class BatchedGoEnv(object):
 
     def __len__(self):
         return self.batch_size
+
+
+class HostStepper(object):
+    """BatchedGoEnv.step for a consumer that lives in host memory: every call moves this ply's actions host->device,
+    plays the ply (finished boards restart first when auto_reset), moves the results device->host and waits for
+    them.  All host buffers are pinned and allocated once, preferably on the GPU's NUMA node (gymgo_b200.hostmem);
+    the whole sequence - copy in, ONE kernel, copies out - is a CUDA graph, so a step costs one graph launch.
+
+        hs = env.host_stepper(returns="obs")
+        hs.actions[:] = ...            # int32 [B] pinned; N*N = pass
+        obs, reward, done = hs.step()  # pinned host tensors, valid until the next step()
+
+    returns: "obs"    the dense [B,6,N,N] observation in env.obs_dtype (what GoEnv.step returns, go_env.py:64)
+             "packed" the packed records [B, rec_bytes] (40x fewer bytes than f32 on 9x9); hs.expand() unpacks them on
+                      the host (gg_host_unpack, multi-threaded C++)
+             "none"   reward and done only (the observation is consumed on the device)
+    reward (f32 [B]) and done (u8 [B]) always come back, in one copy."""
+
+    def __init__(self, env, returns="obs", auto_reset=True, use_cuda_graph=True):
+        if returns not in ("obs", "packed", "none"):
+            raise ValueError("returns must be 'obs', 'packed' or 'none'")
+        self.env, self.returns, self.auto_reset = env, returns, bool(auto_reset)
+        dev = env.engine.device.index
+        b = env.batch_size
+        self.actions = hostmem.pinned_empty((b,), torch.int32, dev)
+        self.actions.fill_(env.size * env.size)
+        self._tail = hostmem.pinned_empty((5 * b,), torch.uint8, dev)
+        self.reward = self._tail[:4 * b].view(torch.float32)
+        self.done = self._tail[4 * b:]
+        self.obs = hostmem.pinned_empty(tuple(env.obs.shape), env.obs_dtype, dev) if returns == "obs" else None
+        self.rec = hostmem.pinned_empty(tuple(env.rec.shape), torch.uint8, dev) if returns == "packed" else None
+        self.h2d_bytes = self.actions.numel() * 4
+        self.d2h_bytes = self._tail.numel() + (self.obs.numel() * self.obs.element_size() if self.obs is not None else 0) \
+            + (self.rec.numel() if self.rec is not None else 0)
+        self._stream = torch.cuda.Stream(device=env.engine.device)
+        self._graph = None
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self.placement = hostmem.describe(dev)
+
+    def _enqueue(self):
+        env = self.env
+        env._step_actions.copy_(self.actions, non_blocking=True)
+        env._enqueue_step(self.auto_reset)
+        if self.obs is not None:
+            self.obs.copy_(env.obs, non_blocking=True)
+        if self.rec is not None:
+            self.rec.copy_(env.rec, non_blocking=True)
+        self._tail.copy_(env._tail, non_blocking=True)
+
+    def step(self):
+        env = self.env
+        env.engine._enter()
+        with torch.cuda.stream(self._stream):
+            if self.use_cuda_graph:
+                if self._graph is None:
+                    scratch = BatchedGoEnv(1, env.size, device=env.engine.device, obs_dtype=env.obs_dtype)
+                    scratch._step_actions.fill_(env.size * env.size)
+                    scratch._enqueue_step(True)                      # load the kernel before capturing
+                    torch.cuda.synchronize(env.engine.device)
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph, stream=self._stream):
+                        self._enqueue()
+                    # capture does not execute: fall through to the first replay
+                self._graph.replay()
+            else:
+                self._enqueue()
+        self._stream.synchronize()
+        first = self.obs if self.returns == "obs" else (self.rec if self.returns == "packed" else None)
+        return first, self.reward, self.done
+
+    def expand(self, out=None, dtype=torch.float32, threads=0):
+        """packed records of the last step -> dense [B,6,N,N] on the HOST (gg_host_unpack; threads=0: all usable cores)"""
+        if self.rec is None:
+            raise ValueError("expand() needs returns='packed'")
+        env = self.env
+        if out is None:
+            out = torch.empty((env.batch_size, 6, env.size, env.size), dtype=dtype)
+        if out.device.type != "cpu" or not out.is_contiguous() or tuple(out.shape) != (env.batch_size, 6, env.size, env.size):
+            raise ValueError("out must be a contiguous host tensor of shape [B,6,N,N]")
+        _cabi.check(env.engine.lib.gg_host_unpack(self.rec.data_ptr(), env.batch_size, env.size, _TORCH2GG[out.dtype],
+                                                  out.data_ptr(), int(threads)))
+        return out

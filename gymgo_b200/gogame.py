@@ -253,29 +253,40 @@ def num_liberties(state):
     return np.count_nonzero(b), np.count_nonzero(w)
 
 
-def _rot90(image, k):
-    return torch.rot90(image, k, dims=(-2, -1)) if _is_torch(image) else np.rot90(image, k, axes=(-2, -1))
+def _flip(image, axis):
+    return torch.flip(image, dims=(axis,)) if _is_torch(image) else np.flip(image, axis)
 
 
-def _flip(image):
-    return torch.flip(image, dims=(-1,)) if _is_torch(image) else np.flip(image, -1)
+def _rot90(image):
+    return torch.rot90(image, 1, dims=(-2, -1)) if _is_torch(image) else np.rot90(image, 1, axes=(-2, -1))
+
+
+def symmetry(image, orientation):
+    """Element `orientation` (0..7) of all_symmetries: bit 0 mirrors the columns, bit 1 mirrors the rows, bit 2 turns
+    the result a quarter counter-clockwise - applied in that order (gogame.py:347-355, :366-380).  The board axes are
+    the last two (the reference names axes 1 and 2 of a [C,N,N] image; leading batch axes are allowed here).
+    gg_symmetry / GoEngine.symmetry apply the same element to packed records."""
+    orientation = int(orientation)
+    if not 0 <= orientation < 8:
+        raise ValueError("orientation must be in 0..7")
+    if orientation & 1:
+        image = _flip(image, -1)
+    if orientation & 2:
+        image = _flip(image, -2)
+    if orientation & 4:
+        image = _rot90(image)
+    return image
 
 
 def random_symmetry(image):
-    """gogame.py:340-355: one of the 8 dihedral transforms of the last two axes (numpy or torch, any leading
-    batch/channel axes; torch tensors stay on their device)."""
-    out = _rot90(image, int(np.random.randint(0, 4)))
-    return _flip(out) if np.random.randint(0, 2) else out
+    """gogame.py:340-355: one uniformly drawn element of all_symmetries (one np.random.randint(0, 8) draw, so a
+    seeded numpy stream picks the same orientation as the reference)."""
+    return symmetry(image, np.random.randint(0, 8))
 
 
 def all_symmetries(image):
-    """gogame.py:358-382: the 8 dihedral transforms (numpy or torch)."""
-    out = []
-    for flip in (False, True):
-        base = _flip(image) if flip else image
-        for k in range(4):
-            out.append(_rot90(base, k))
-    return out
+    """gogame.py:358-382: the 8 dihedral transforms, in the reference's order (numpy or torch)."""
+    return [symmetry(image, i) for i in range(8)]
 
 
 def random_weighted_action(move_weights):
@@ -289,16 +300,35 @@ def random_action(state):
     return random_weighted_action(np.asarray(valid_moves(state).cpu() if _is_torch(state) else valid_moves(state)))
 
 
+_STONES = {0: "\u25cb", 1: "\u25cf"}                       # glyph of a black / white stone
+_EDGE_LINK, _INNER_LINK = "\u2550", "\u2500"               # horizontal link on the first/last row, elsewhere
+_CORNERS = ("\u2554\u2557", "\u255f\u2562", "\u255a\u255d")   # (left, right) end glyphs: first row, inner rows, last row
+_JOINTS = ("\u2564", "\u253c", "\u2567")                        # inner-column glyph: first row, inner rows, last row
+
+
 def str(state):  # noqa: A001 - the reference exports this name (gogame.py:407-468)
-    """ASCII rendering (presentation only): B/W stones, '.' empty, then turn / pass / done / areas."""
+    """Text rendering, character for character the reference's: a tab-indented column header, one line per row
+    (row index, tab, box-drawing grid with stones), then the turn / game-state line and the area line."""
     st = np.asarray(state.cpu() if _is_torch(state) else state)
     n = st.shape[1]
-    lines = ["   " + " ".join("%d" % (c % 10) for c in range(n))]
+    last = n - 1
+    lines = ["\t" + "".join("{:<2d}".format(c) for c in range(n))]
     for r in range(n):
-        row = ["B" if st[0, r, c] else "W" if st[1, r, c] else "." for c in range(n)]
-        lines.append("%2d %s" % (r, " ".join(row)))
-    b, w = areas(st)
-    lines.append("Turn: %s, Last Turn Passed: %s, Game Over: %s" % (
-        "WHITE" if turn(st) else "BLACK", bool(prev_player_passed(st)), bool(game_ended(st))))
-    lines.append("Black Area: %d, White Area: %d" % (int(b), int(w)))
+        band = 0 if r == 0 else (2 if r == last else 1)
+        link = _INNER_LINK if band == 1 else _EDGE_LINK
+        cells = []
+        for c in range(n):
+            colour = 0 if st[govars.BLACK, r, c] == 1 else (1 if st[govars.WHITE, r, c] == 1 else None)
+            if colour is not None:
+                glyph = _STONES[colour]
+            elif c == 0 or c == last:
+                glyph = _CORNERS[band][0 if c == 0 else 1]
+            else:
+                glyph = _JOINTS[band]
+            cells.append(glyph if c == last else glyph + link)
+        lines.append("{}\t{}".format(r, "".join(cells)))
+    black_area, white_area = areas(st)
+    phase = "END" if game_ended(st) else ("PASSED" if prev_player_passed(st) else "ONGOING")
+    lines.append("\tTurn: {}, Game State (ONGOING|PASSED|END): {}".format("WHITE" if turn(st) else "BLACK", phase))
+    lines.append("\tBlack Area: {}, White Area: {}".format(int(black_area), int(white_area)))
     return "\n".join(lines) + "\n"

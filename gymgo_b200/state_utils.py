@@ -7,8 +7,9 @@ passes (`state_utils.py:24-250`); here they are fused inside the step kernel (gg
     code path: the legality mask "after `player` moved" is exactly what a pass by `player` recomputes
     (gogame.py:48-53,78), so we set the turn plane to `player`, pass on the GPU and read the INVD plane.
   * adj_data / batch_adj_data (state_utils.py:214-232), set_turn / batch_set_turn (:235-250): tiny array helpers.
-  * update_pieces / batch_update_pieces (:159-211) have no standalone equivalent - capture removal happens
-    inside gg_step; calling them raises NotImplementedError with that pointer."""
+  * update_pieces / batch_update_pieces (:159-211): the capture routine of the step kernel as a stand-alone launch
+    (gg_update_pieces); the state array is updated in place and the killed groups come back as coordinate arrays
+    in the reference's order (groups by their first stone in raster order, stones in raster order)."""
 import numpy as np
 
 from . import govars
@@ -62,8 +63,57 @@ def batch_set_turn(batch_state):
     batch_state[:, govars.TURN_CHNL] = 1 - batch_state[:, govars.TURN_CHNL]
 
 
-def update_pieces(*args, **kwargs):
-    raise NotImplementedError("capture removal is fused into the step kernel (gg_step / gogame.next_state)")
+def _split_groups(dead):
+    """bool [N,N] plane of removed stones -> list of [k,2] coordinate arrays, one per 4-connected group, ordered like
+    ndimage.label numbers them (by first stone in raster order); stones inside a group in raster order (np.argwhere)"""
+    groups = []
+    left = dead.copy()
+    n = dead.shape[0]
+    while left.any():
+        r, c = np.argwhere(left)[0]
+        member = np.zeros_like(left)
+        frontier = [(int(r), int(c))]
+        member[r, c] = True
+        while frontier:
+            y, x = frontier.pop()
+            for dy, dx in neighbor_deltas:
+                v, u = y + dy, x + dx
+                if 0 <= v < n and 0 <= u < n and left[v, u] and not member[v, u]:
+                    member[v, u] = True
+                    frontier.append((v, u))
+        groups.append(np.argwhere(member))
+        left &= ~member
+    return groups
 
 
-batch_update_pieces = update_pieces
+def batch_update_pieces(batch_non_pass, batch_state, batch_adj_locs, batch_player):
+    """state_utils.py:183-211: for the boards `batch_non_pass` of `batch_state` (in place), remove the groups of the
+    opponent of `batch_player[i]` that touch `batch_adj_locs[i]` and have no liberty; -> list (per listed board) of
+    lists of killed groups."""
+    import torch
+    idx = np.asarray(batch_non_pass, dtype=np.int64).reshape(-1)
+    if len(idx) == 0:
+        return []
+    n = batch_state.shape[-1]
+    eng = _engine(n)
+    players = np.asarray(batch_player, dtype=np.int64).reshape(-1)
+    if len(players) != len(idx):
+        players = players[idx]                      # the reference passes the full-batch vector (state_utils.py:184)
+    touch = np.zeros((len(idx), govars.NUM_CHNLS, n, n), dtype=np.uint8)
+    for i, locs in enumerate(batch_adj_locs):
+        locs = np.asarray(locs, dtype=np.int64).reshape(-1, 2)
+        touch[i, govars.BLACK, locs[:, 0], locs[:, 1]] = 1
+    sub = np.ascontiguousarray(np.asarray(batch_state)[idx] != 0).astype(np.uint8)
+    rec = eng.pack(torch.from_numpy(sub).to(eng.device))
+    killed = eng.update_pieces(rec, eng.pack(torch.from_numpy(touch).to(eng.device)), players)
+    dead = eng.unpack(killed, dtype=torch.uint8)[:, govars.BLACK].cpu().numpy().astype(bool)
+    out = []
+    for i, b in enumerate(idx):
+        batch_state[b, 1 - int(players[i])][dead[i]] = 0
+        out.append(_split_groups(dead[i]))
+    return out
+
+
+def update_pieces(state, adj_locs, player):
+    """state_utils.py:159-180 (state modified in place; returns the list of killed groups)"""
+    return batch_update_pieces([0], state[None], [adj_locs], [player])[0]

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GG_VERSION 100 /* 0.1.0 */
+#define GG_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define GG_API __attribute__((visibility("default")))
@@ -70,6 +70,16 @@ extern "C" {
 /* gg_step / gg_children option bits */
 #define GG_STEP_CANONICAL 1u   /* canonical=True of gogame.next_state (gogame.py:83-85, :313-321) */
 #define GG_STEP_REFUSE_DONE 2u /* GoEnv.step's `assert not self.done` (go_env.py:54) */
+#define GG_STEP_AUTO_RESET 4u  /* gg_step only: a board whose record is finished is first reset to gogame.init_state
+                                * (GoEnv.reset, go_env.py:40-47), then plays its action - the vector-env loop in ONE launch */
+#define GG_STEP_RESET_SKIPS_ACTION 8u /* with GG_STEP_AUTO_RESET: a board that was just reset does NOT play its action
+                                       * this ply (status OK, empty board out) - gymnasium's next-step autoreset */
+
+/* rollout kernels (gg_rollout_with); all three produce identical results */
+#define GG_KERNEL_AUTO (-1)    /* chosen per (n, batch) from measurements: what gg_rollout uses */
+#define GG_KERNEL_LANES 0      /* k_rollout: a board spread over adjacent lanes of a warp */
+#define GG_KERNEL_THREAD 1     /* k_rollout_tpb: one board per thread */
+#define GG_KERNEL_LANES_WS 2   /* k_rollout_ws: lane-sliced boards, observations written by dedicated emitter warps */
 
 GG_API int gg_version(void);
 GG_API const char *gg_last_cuda_error(void);
@@ -136,9 +146,23 @@ GG_API int gg_rollout(void *rec, int64_t batch, int n, uint64_t seed, uint64_t b
                       int plies_per_launch, int32_t *actions_log, void *obs_ring_buf, int obs_dtype, int obs_ring,
                       uint8_t *done_log, float *reward_log, int reward_mode, float komi, void *stream);
 
-/* Name of the kernel gg_rollout uses for (n, batch): small boards with large batches run one board per thread
- * (k_rollout_tpb), everything else spreads a board over adjacent lanes (k_rollout).  Same results either way. */
+/* gg_rollout with an explicit kernel choice (GG_KERNEL_*): for A/B measurements and the kernel-vs-kernel parity
+ * tests.  gg_rollout(...) == gg_rollout_with(GG_KERNEL_AUTO, ...). */
+GG_API int gg_rollout_with(int kernel, void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0,
+                           int steps, int plies_per_launch, int32_t *actions_log, void *obs_ring_buf, int obs_dtype,
+                           int obs_ring, uint8_t *done_log, float *reward_log, int reward_mode, float komi, void *stream);
+
+/* Name of the kernel GG_KERNEL_AUTO resolves to for (n, batch), and the name of kernel `kernel`. */
 GG_API const char *gg_rollout_kernel(int n, int64_t batch);
+GG_API const char *gg_kernel_name(int kernel);
+
+/* Capture removal alone: on board b every group of colour 1 - player[b] that touches a point of `touch` and has no
+ * empty neighbour is removed from rec[b] (in place; only that colour's plane changes).  `touch` and `killed` are
+ * record arrays used as plane carriers: the BLACK plane of touch[b] holds the adjacent locations, the BLACK plane of
+ * killed[b] receives the removed stones (the rest of killed[b] is zeroed).
+ * Replaces: state_utils.update_pieces / batch_update_pieces (state_utils.py:159-211). */
+GG_API int gg_update_pieces(void *rec, const void *touch, const int32_t *player, void *killed, int64_t batch, int n,
+                            void *stream);
 
 /* The sampler alone (no reset, no step): actions_out[b] = uniformly random valid action of board b.
  * Replaces: GoEnv.uniform_random_action / gogame.random_action (go_env.py:78-81, gogame.py:395-404). */
@@ -169,9 +193,17 @@ GG_API int gg_areas(const void *rec, int64_t batch, int n, int32_t *out, void *s
 GG_API int gg_canonical(const void *rec_in, void *rec_out, int64_t batch, int n, void *stream);
 
 /* One of the 8 dihedral transforms applied to packed records (stone and invalid planes; flags copied), out of
- * place.  sym = 4*flip + k reproduces element `sym` of gogame.all_symmetries (gogame.py:358-382):
- * np.rot90(np.flip(x, -1) if flip else x, k).  Replaces: random_symmetry / all_symmetries (gogame.py:340-382). */
+ * place.  `sym` (0..7) is the index into gogame.all_symmetries (gogame.py:358-382): bit 0 mirrors the columns
+ * (np.flip axis 2), bit 1 mirrors the rows (np.flip axis 1), bit 2 turns the result a quarter counter-clockwise
+ * (np.rot90 over axes 1,2), applied in that order.  Pinned by tests/golden/misc.npz (outputs of the reference).
+ * Replaces: random_symmetry / all_symmetries (gogame.py:340-382). */
 GG_API int gg_symmetry(const void *rec_in, void *rec_out, int64_t batch, int n, int sym, void *stream);
+
+/* HOST codec (the only entry point that takes host pointers and runs on the CPU): packed records in host memory ->
+ * dense [B,6,N,N] of dtype in host memory, `threads` worker threads (<= 0: all hardware threads, capped at 64).
+ * For consumers that fetch the packed records over PCIe instead of the 40x larger dense observation
+ * (BatchedGoEnv.host_stepper(returns="packed")).  No Go rules run here - it is gg_unpack's layout, nothing else. */
+GG_API int gg_host_unpack(const void *rec_host, int64_t batch, int n, int dtype, void *dense_host, int threads);
 
 #ifdef __cplusplus
 }

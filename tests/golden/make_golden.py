@@ -17,6 +17,10 @@ Outputs (small, bit-packed .npz files next to this script):
                      stale INVD planes, moves on finished games) stepped through the reference.
   children_n{N}.npz  reference gogame.children(state, canonical, padded=True) on mid-game parents.
   env_n7.npz         GoEnv-level behaviour: rewards ('real', 'heuristic', komi), info dict values.
+  misc.npz           the helpers around the step: gogame.all_symmetries (element by
+                     element, N in {5,9,19}), gogame.random_symmetry under seeded numpy streams,
+                     gogame.str renderings, gogame.liberties, and state_utils.update_pieces /
+                     adj_data on capturing and non-capturing placements (new state + killed groups).
 
 Only OUTPUTS of the reference are stored, never its code.  All states are 0/1 so
 they are stored with np.packbits; `tests/golden_io.py` is the reader.
@@ -287,7 +291,90 @@ def gen_env():
     save("env_n7.npz", **out)
 
 
+# ------------------------------------------------------------------------ misc
+def _midgame(n, plies, rng):
+    state = gogame.init_state(n)
+    for _ in range(plies):
+        a = int(rng.choice(np.argwhere(gogame.valid_moves(state)).flatten()))
+        nxt = gogame.next_state(state, a)
+        if gogame.game_ended(nxt):
+            break
+        state = nxt
+    return state
+
+
+def gen_misc():
+    out = {}
+    # (1) all_symmetries element by element + random_symmetry under seeded streams
+    for n, plies in ((5, 14), (9, 50), (19, 220)):
+        rng = np.random.RandomState(5000 + n)
+        img = _midgame(n, plies, rng)
+        syms = np.stack([np.ascontiguousarray(x) for x in gogame.all_symmetries(img)])
+        out["sym_n%d__image" % n], out["sym_n%d__image_shape" % n] = pack_states(img)
+        out["sym_n%d__all" % n], out["sym_n%d__all_shape" % n] = pack_states(syms)
+        picks = []
+        for seed in range(24):
+            np.random.seed(seed)
+            picks.append(np.ascontiguousarray(gogame.random_symmetry(img)))
+        out["sym_n%d__random" % n], out["sym_n%d__random_shape" % n] = pack_states(np.stack(picks))
+    # (2) str renderings, liberties
+    texts, tstates, libs = [], [], []
+    for n, plies in ((3, 5), (5, 10), (7, 30), (7, 60), (9, 70)):
+        rng = np.random.RandomState(5100 + n + plies)
+        st = _midgame(n, plies, rng)
+        for extra in ([], [n * n], [n * n, n * n]):
+            s2 = st
+            for a in extra:
+                s2 = gogame.next_state(s2, a)
+            texts.append(gogame.str(s2))
+            key = "text%d" % (len(texts) - 1)
+            out[key + "__state"], out[key + "__shape"] = pack_states(s2)
+            lb, lw = gogame.liberties(s2)
+            out[key + "__liberties"], out[key + "__liberties_shape"] = pack_states(np.stack([lb, lw]).astype(np.float64))
+    out["texts"] = np.array(texts)
+    # (3) update_pieces / adj_data: place a stone like next_state does (gogame.py:61-69) and let the reference
+    # remove the captured groups; killed groups are stored as a label plane (k-th returned group -> value k+1)
+    cases = 0
+    for n, count in ((5, 60), (7, 60), (9, 60), (19, 12)):
+        rng = np.random.RandomState(5200 + n)
+        state = gogame.init_state(n)
+        got = 0
+        while got < count:
+            vm = gogame.valid_moves(state)
+            a = int(rng.choice(np.argwhere(vm).flatten()))
+            if a < n * n:
+                player = gogame.turn(state)
+                r, c = a // n, a % n
+                placed = np.copy(state)
+                placed[player, r, c] = 1
+                adj, surrounded = state_utils.adj_data(placed, np.array([r, c]), player)
+                after = np.copy(placed)
+                killed = state_utils.update_pieces(after, adj, player)
+                # keep every capture and a thinning of the quiet moves
+                if killed or rng.randint(4) == 0:
+                    label = np.zeros((n, n), dtype=np.int64)
+                    for k, grp in enumerate(killed):
+                        label[grp[:, 0], grp[:, 1]] = k + 1
+                    key = "up%d" % cases
+                    out[key + "__before"], out[key + "__shape"] = pack_states(placed)
+                    out[key + "__after"], _ = pack_states(after)
+                    out[key + "__killed"] = label
+                    out[key + "__meta"] = np.array([n, r, c, player, int(bool(surrounded)), len(killed)], dtype=np.int64)
+                    out[key + "__adj"] = np.asarray(adj, dtype=np.int64)
+                    cases += 1
+                    got += 1
+            state = gogame.next_state(state, a)
+            if gogame.game_ended(state):
+                state = gogame.init_state(n)
+    out["update_cases"] = np.array(cases, dtype=np.int64)
+    save("misc.npz", **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["misc"]:
+        gen_misc()
+        raise SystemExit(0)
+    gen_misc()
     gen_kats()
     gen_traj()
     gen_soup()

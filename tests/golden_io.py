@@ -67,6 +67,40 @@ def env_games():
     return out
 
 
+def symmetries(n):
+    """-> (image [6,N,N], all [8,6,N,N] = reference all_symmetries(image), random [24,6,N,N] = reference
+    random_symmetry(image) after np.random.seed(0..23))"""
+    z = load("misc.npz")
+    k = "sym_n%d__" % n
+    return (_unpack(z[k + "image"], z[k + "image_shape"]), _unpack(z[k + "all"], z[k + "all_shape"]),
+            _unpack(z[k + "random"], z[k + "random_shape"]))
+
+
+def texts():
+    """-> list of (state [6,N,N], reference gogame.str(state), liberties [2,N,N])"""
+    z = load("misc.npz")
+    out = []
+    for i, text in enumerate(z["texts"]):
+        k = "text%d__" % i
+        out.append((_unpack(z[k + "state"], z[k + "shape"]), str(text),
+                    _unpack(z[k + "liberties"], z[k + "liberties_shape"])))
+    return out
+
+
+def update_pieces_cases():
+    """-> list of dict(before, after [6,N,N], killed [N,N] label plane, n, point, player, surrounded, groups, adj)"""
+    z = load("misc.npz")
+    out = []
+    for i in range(int(z["update_cases"])):
+        k = "up%d__" % i
+        n, r, c, player, surrounded, groups = (int(x) for x in z[k + "meta"])
+        out.append(dict(before=_unpack(z[k + "before"], z[k + "shape"]), after=_unpack(z[k + "after"], z[k + "shape"]),
+                        killed=z[k + "killed"], n=n, point=(r, c), player=player, surrounded=bool(surrounded),
+                        groups=groups, adj=z[k + "adj"]))
+    return out
+
+
+SYM_SIZES = (5, 9, 19)
 TRAJ_SIZES = (3, 5, 7, 9, 13, 19)
 SOUP_SIZES = (2, 4, 5, 9, 19)
 CHILDREN_SIZES = (3, 5, 7, 9, 19)

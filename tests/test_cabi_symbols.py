@@ -21,7 +21,7 @@ def test_header_symbols_are_exported():
     assert len(names) >= 18 and set(names) == set(_cabi.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.gg_version() == 100
+    assert lib.gg_version() == _cabi.GG_VERSION == 200
 
 
 def test_layout_and_argument_errors_without_gpu():
@@ -41,6 +41,47 @@ def test_layout_and_argument_errors_without_gpu():
     assert lib.gg_step(addr, addr, addr, None, -1, 9, 0, None, 0, None, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
     assert lib.gg_areas((addr | 15) + 1 + 4, 4, 9, addr, None) == _cabi.GG_EALIGN
     assert lib.gg_rollout(addr, 4, 9, 0, 0, 0, 3, 0, None, None, 0, 0, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
+
+
+def test_rollout_kernel_choice_and_new_argument_checks():
+    from gymgo_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.gg_kernel_name(_cabi.GG_KERNEL_THREAD).decode().startswith("k_rollout_tpb")
+    assert lib.gg_kernel_name(_cabi.GG_KERNEL_LANES_WS).decode().startswith("k_rollout_ws")
+    assert lib.gg_kernel_name(7) == b""
+    assert lib.gg_rollout_kernel(9, 65536).decode().startswith("k_rollout_tpb")      # configs[1]
+    assert "tpb" not in lib.gg_rollout_kernel(19, 16384).decode()                      # configs[2]
+    buf = ctypes.create_string_buffer(64)
+    addr = ctypes.addressof(buf)
+    bad_kernel = lib.gg_rollout_with(5, addr, 4, 9, 0, 0, 0, 3, 1, None, None, 0, 0, None, None, 0, 0.0, None)
+    assert bad_kernel == _cabi.GG_EINVAL
+    assert lib.gg_step(addr, addr, addr, None, 4, 9, 16, None, 0, None, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
+    assert lib.gg_update_pieces(addr, addr, addr, addr, 4, 9, None) == _cabi.GG_EINVAL       # killed aliases rec
+    assert lib.gg_update_pieces(None, addr, addr, addr, 4, 9, None) == _cabi.GG_EINVAL
+    assert lib.gg_host_unpack(None, 4, 9, 1, addr, 1) == _cabi.GG_EINVAL
+    assert lib.gg_host_unpack(addr, 4, 30, 1, addr, 1) == _cabi.GG_ESIZE
+
+
+def test_host_codec_matches_the_record_layout():
+    """gg_host_unpack (the only host-side entry point: packed records in host memory -> dense) against the host
+    simulator's independent packer, every size and dtype"""
+    import numpy as np
+    import hostsim
+    from gymgo_b200 import _cabi
+    lib = _cabi.lib()
+    for n in range(2, 20):
+        rng = np.random.RandomState(n)
+        st = (rng.uniform(size=(4100, 6, n, n)) < 0.5).astype(np.uint8)
+        st[:, [2, 4, 5]] = rng.randint(2, size=(4100, 3))[:, :, None, None]
+        rec = np.ascontiguousarray(hostsim.pack(st)).view(np.uint8)
+        for dt, code in ((np.uint8, _cabi.GG_U8), (np.float32, _cabi.GG_F32), (np.float64, _cabi.GG_F64)):
+            for threads in (1, 3):
+                out = np.empty((4100, 6, n, n), dtype=dt)
+                assert lib.gg_host_unpack(rec.ctypes.data, 4100, n, code, out.ctypes.data, threads) == 0
+                assert np.array_equal(out, st.astype(dt)), (n, dt)
+        half = np.empty((4100, 6, n, n), dtype=np.uint16)
+        assert lib.gg_host_unpack(rec.ctypes.data, 4100, n, _cabi.GG_BF16, half.ctypes.data, 2) == 0
+        assert np.array_equal(half, st.astype(np.uint16) * 0x3F80)
 
 
 def test_no_cpu_fallback():

@@ -185,9 +185,10 @@ def test_cuda_graph_capture_of_step_calls():
     assert torch.equal(rec, want_rec) and torch.equal(obs, want_obs)
 
 
-def test_vector_env_autoreset_and_masks():
+@pytest.mark.parametrize("mode", ("next_step", "play_on_reset"))
+def test_vector_env_autoreset_and_masks(mode):
     from gymgo_b200.envs import GoVectorEnv
-    venv = GoVectorEnv(128, 5, reward_method="real", obs_dtype=torch.uint8, seed=4)
+    venv = GoVectorEnv(128, 5, reward_method="real", obs_dtype=torch.uint8, seed=4, autoreset_mode=mode)
     obs, info = venv.reset()
     assert obs.shape == (128, 6, 5, 5) and not obs.any() and info["action_mask"].all()
     ref = [og.EnvOracle(5) for _ in range(128)]
@@ -200,14 +201,72 @@ def test_vector_env_autoreset_and_masks():
         assert not trunc.any() and not info["status"].any()
         for i in range(128):
             if finished_before[i]:
-                ref[i].reset()
-            s, r, d, _ = ref[i].step(int(a[i]))
+                s, r, d = ref[i].reset(), 0, False
+                if mode == "play_on_reset":                     # the action is played on the fresh board
+                    s, r, d, _ = ref[i].step(int(a[i]))
+            else:
+                s, r, d, _ = ref[i].step(int(a[i]))
             assert np.array_equal(obs[i].cpu().numpy(), s.astype(np.uint8))
             assert float(rew[i]) == float(r) and bool(term[i]) == bool(d)
             assert np.array_equal(info["action_mask"][i].cpu().numpy(), og.valid_moves(s).astype(np.uint8))
             finished_before[i] = bool(d)
         ended += int(term.sum())
     assert ended > 0
+    # copy=True hands out tensors that survive the next step
+    keep = GoVectorEnv(16, 5, seed=1, copy=True)
+    keep.reset()
+    o1, r1, *_ = keep.step(keep.sample_actions())
+    snap = o1.clone()
+    keep.step(keep.sample_actions())
+    assert torch.equal(o1, snap)
+
+
+def test_step_auto_reset_flag_equals_reset_then_step():
+    """GG_STEP_AUTO_RESET inside gg_step == gg_reset(mask=done) followed by gg_step (the two-launch loop of round 1)"""
+    from gymgo_b200.engine import GoEngine
+    e = GoEngine(9, "cuda:0")
+    a, b = e.new_records(5000), e.new_records(5000)
+    done = torch.zeros(5000, dtype=torch.uint8, device="cuda")
+    for t in range(200):
+        acts = e.sample_legal(a, 3, 0, t)
+        acts = torch.where(torch.arange(5000, device="cuda") % 4 == 0, torch.full_like(acts, 81), acts)   # many passes
+        e.reset(b, done)
+        rb = e.step(b, acts, out=b, refuse_done=True, obs_dtype=torch.uint8, want_done=True, reward_mode=1)
+        ra = e.step(a, acts, out=a, refuse_done=True, auto_reset=True, obs_dtype=torch.uint8, want_done=True, reward_mode=1)
+        done = rb["done"]
+        for k in ("status", "obs", "done", "reward"):
+            assert torch.equal(ra[k], rb[k]), (t, k)
+        assert torch.equal(a, b)
+    assert bool(done.any())
+    with pytest.raises(ValueError):
+        e.reset(a, torch.zeros(17, dtype=torch.uint8))              # mask must be [B]
+    with pytest.raises(ValueError):
+        e.unpack(a, out=torch.empty((5, 6, 9, 9), device="cuda"))   # out must be [B,6,N,N]
+
+
+@pytest.mark.parametrize("returns,graph", (("obs", True), ("obs", False), ("packed", True), ("none", True)))
+def test_host_stepper_matches_device_step(returns, graph):
+    """the host-buffer step (pinned actions in, pinned results out, one CUDA graph) == BatchedGoEnv.step"""
+    from gymgo_b200.envs import BatchedGoEnv
+    env = BatchedGoEnv(3000, 9, reward_method="heuristic", komi=0.5, obs_dtype=torch.float32)
+    ref = BatchedGoEnv(3000, 9, reward_method="heuristic", komi=0.5, obs_dtype=torch.float32)
+    hs = env.host_stepper(returns=returns, use_cuda_graph=graph)
+    assert hs.h2d_bytes == 3000 * 4
+    assert hs.d2h_bytes == 3000 * 5 + {"obs": 3000 * 6 * 81 * 4, "packed": 3000 * env.engine.rec_bytes, "none": 0}[returns]
+    for t in range(140):
+        acts = ref.engine.sample_legal(ref.rec, 9, 0, t)
+        hs.actions.copy_(acts.cpu())
+        first, rew, done = hs.step()
+        o, r, d, _ = ref.step(acts, auto_reset=True)
+        assert not first.is_cuda if first is not None else True
+        assert torch.equal(rew, r.cpu()) and torch.equal(done, d.cpu())
+        if returns == "obs":
+            assert torch.equal(first, o.cpu())
+        elif returns == "packed":
+            assert torch.equal(first, ref.rec.cpu())
+            assert torch.equal(hs.expand(), o.cpu())
+            assert torch.equal(hs.expand(dtype=torch.uint8, threads=3), o.cpu().to(torch.uint8))
+    assert torch.equal(env.rec, ref.rec) and bool(ref.done.any())
 
 
 @pytest.mark.parametrize("n", (5, 9, 13, 19))

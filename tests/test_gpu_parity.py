@@ -179,50 +179,51 @@ def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
     assert all(bool((ring[s] == 7).all()) for s in untouched)
 
 
-@pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 141), (13, 97), (16, 33)))
+@pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 141), (13, 97), (16, 33), (2, 50)))
 @pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.float16))
-def test_thread_per_board_variant_matches(eng, n, boards, dtype, monkeypatch):
-    """the thread-per-board rollout kernel is bit-identical to the lane-sliced one (GG_ROLLOUT_VARIANT forces either)"""
+def test_rollout_kernels_are_bit_identical(eng, n, boards, dtype):
+    """the three persistent rollout kernels - lane-sliced, thread-per-board, lane-sliced with emitter warps - produce
+    the same records, observations and logs (gg_rollout_with forces each)"""
+    from gymgo_b200 import _cabi
     e = eng(n)
     outs = []
-    for variant in ("0", "1"):
-        monkeypatch.setenv("GG_ROLLOUT_VARIANT", variant)
+    for kernel in (_cabi.GG_KERNEL_LANES, _cabi.GG_KERNEL_THREAD, _cabi.GG_KERNEL_LANES_WS):
         rec = e.new_records(boards)
         ring = e.empty((23, boards, 6, n, n), dtype=dtype)
         ring.fill_(3)
         acts = torch.empty((22, boards), dtype=torch.int32, device="cuda")
         dones = torch.empty((22, boards), dtype=torch.uint8, device="cuda")
         rews = torch.empty((22, boards), dtype=torch.float32, device="cuda")
-        e.rollout(rec, 5, 77, 0, 150, plies_per_launch=50)
+        e.rollout(rec, 5, 77, 0, 150, plies_per_launch=50, kernel=kernel)
         e.rollout(rec, 5, 77, 150, 22, plies_per_launch=6, actions_log=acts, obs_ring=ring, done_log=dones,
-                  reward_log=rews, reward_mode=2, komi=1.5)
+                  reward_log=rews, reward_mode=2, komi=1.5, kernel=kernel)
         torch.cuda.synchronize()
         outs.append((rec, ring, acts, dones, rews))
-    for x, y in zip(*outs):
-        assert torch.equal(x, y)
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("n,boards,k", ((19, 141, 2), (19, 77, 3), (19, 50, 4), (13, 97, 2), (16, 33, 3), (11, 200, 2)))
-def test_sliced_variant_matches(eng, n, boards, k, monkeypatch):
-    """k_rollout_sliced (K plane words per lane, developer variant 2) is bit-identical to the default kernel"""
+@pytest.mark.parametrize("n,boards,ppl,ring", ((19, 1000, 7, 3), (19, 64, 32, 32), (13, 500, 5, 2), (9, 2000, 9, 4), (6, 77, 3, 1)))
+def test_emitter_warp_kernel_long_launches(eng, n, boards, ppl, ring):
+    """k_rollout_ws with many plies per launch and small observation rings (buffer hand-over between rule and emitter
+    warps wraps around many times): every ring slot equals the observation the single-ply kernel writes"""
+    from gymgo_b200 import _cabi
     e = eng(n)
-    outs = []
-    for variant in ("0", "2"):
-        monkeypatch.setenv("GG_ROLLOUT_VARIANT", variant)
-        monkeypatch.setenv("GG_ROLLOUT_K", str(k))
-        rec = e.new_records(boards)
-        ring = e.empty((9, boards, 6, n, n), dtype=torch.float32)
-        ring.fill_(3)
-        acts = torch.empty((22, boards), dtype=torch.int32, device="cuda")
-        dones = torch.empty((22, boards), dtype=torch.uint8, device="cuda")
-        rews = torch.empty((22, boards), dtype=torch.float32, device="cuda")
-        e.rollout(rec, 5, 77, 0, 250, plies_per_launch=50)
-        e.rollout(rec, 5, 77, 250, 22, plies_per_launch=6, actions_log=acts, obs_ring=ring, done_log=dones,
-                  reward_log=rews, reward_mode=1, komi=0.5)
-        torch.cuda.synchronize()
-        outs.append((rec, ring, acts, dones, rews))
-    for x, y in zip(*outs):
-        assert torch.equal(x, y)
+    a, b = e.new_records(boards), e.new_records(boards)
+    obs_ring = e.empty((ring, boards, 6, n, n), dtype=torch.float32)
+    one = e.empty((boards, 6, n, n), dtype=torch.float32)
+    t = 0
+    for launch in range(6):
+        e.rollout(a, 11, 5, t, ppl, plies_per_launch=ppl, obs_ring=obs_ring, kernel=_cabi.GG_KERNEL_LANES_WS)
+        last = {}
+        for p in range(ppl):
+            e.rollout_step(b, 11, 5, t + p, obs=one)
+            last[(t + p) % ring] = one.clone()
+        for slot, want in last.items():
+            assert torch.equal(obs_ring[slot], want), (launch, slot)
+        t += ppl
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("n", golden_io.CHILDREN_SIZES)
