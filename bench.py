@@ -4,16 +4,30 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 9x9|19x19]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE ply on every board of the batch: one launch of the fused kernel gg_rollout_step
-(auto-reset finished boards -> uniform-random legal action incl. pass -> ply -> write the packed record and
-the float32 6xNxN observation).  Workload at N=1 = BASELINE.json configs[1]: 9x9, 65,536 boards
-(`--workload 19x19` = configs[2]: 16,384 boards).  Multi-GPU: the same per-GPU batch on every rank (weak
-scaling), boards keyed by global index so trajectories do not depend on the sharding; no collective in the
-timed loop, one all-gather of (plies, seconds) at the end.
+A "step" is ONE ply on every board of the batch (auto-reset finished boards -> uniform-random legal action incl.
+pass -> ply -> packed record, float32 6xNxN observation, action, reward, done).  Workload at N=1 = BASELINE.json
+configs[1]: 9x9, 65,536 boards (`--workload 19x19` = configs[2]: 16,384 boards).
 
-Rank 0 prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU arm instead: the
-reference's own algorithm (the numpy/scipy port in oracle/gogame_np.py - the reference is pure Python and
-cannot travel to the GPU box) on every host core.
+What is timed, whatever K/W the caller passes (SURVEY.md 8d defines the metric at steady state):
+  1. untimed set-up: the boards are pre-rolled PREROLL plies so that game phases are de-synchronised (9x9 games
+     last ~124 plies, 19x19 ~700) - declared in `config.preroll_plies`;
+  2. W warm-up steps with all outputs;
+  3. the timed region: R repetitions of exactly K steps, R chosen (from an untimed trial, same R on every rank)
+     so that the region lasts >= MIN_TIMED_MS of device time; `ms_per_step` is the mean over R*K steps.
+The persistent kernel plays min(K, plies_per_launch) plies per launch into an observation ring with one slot per
+ply of a launch: every observation of a launch stays readable until the next launch (ring bytes >> L2).
+
+The JSON line also carries `extra`: the other BASELINE configs measured in the same run - 19x19 x 16,384
+(configs[2]; per GPU this is configs[4] at --gpus 8) and children() of 4,096 9x9 parents (configs[3]) - and `e2e`:
+the same metric through the public host-buffer API (BatchedGoEnv.host_stepper: pinned actions in, pinned f32
+observation + reward + done out, copies inside the timed region) with its cheaper variants next to it.
+
+Multi-GPU: the same per-GPU batch on every rank (weak scaling), boards keyed by global index so trajectories do not
+depend on the sharding; no collective in the timed loop, all-gathers of counters before and after it.
+
+`--impl reference` times the CPU arm instead: the reference's own algorithm (the numpy/scipy port in
+oracle/gogame_np.py - the reference is pure Python and cannot travel to the GPU box; the port is 1.35-1.5x FASTER
+than the real reference measured in the build container, so ratios against it are conservative) on every host core.
 """
 import argparse
 import json
@@ -32,6 +46,8 @@ WORKLOADS = {
     "19x19": dict(size=19, boards=16384, name="19x19 x 16,384 boards, uniform-random-legal rollout (configs[2])"),
 }
 SEED = 0
+PREROLL = 256            # untimed set-up plies (>= the 200 SURVEY.md 8d asks for)
+MIN_TIMED_MS = 60.0      # the timed region is repeated until it lasts at least this long
 
 
 def algorithmic_bytes_per_ply(n, obs_bytes_per_elem):
@@ -41,11 +57,13 @@ def algorithmic_bytes_per_ply(n, obs_bytes_per_elem):
     return 2 * r + 4 + 6 * n * n * obs_bytes_per_elem
 
 
-def profiled_traffic(workload, obs, plies_per_launch):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this configuration (or None)"""
+def profiled_traffic(size, obs, plies_in_launch):
+    """DRAM bytes of one launch of the dominant kernel, scaled from the committed ncu capture of this configuration
+    (profiles/traffic.json: bytes per ply of a 32-ply launch) to the plies this run puts in a launch; None if no capture"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)["%s/%s/%d" % (workload, obs, plies_per_launch)]["dram_bytes_per_launch"]
+            row = json.load(f)["%dx%d/%s" % (size, size, obs)]
+        return {"dram_bytes_per_launch": int(row["dram_bytes_per_ply"] * plies_in_launch), "source": row["source"]}
     except Exception:  # noqa: BLE001
         return None
 
@@ -70,7 +88,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -88,7 +106,7 @@ class ClockSampler(object):
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.2] or self.rows
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.05] or self.rows
         for _, line in rows:
             f = [x.strip() for x in line.split(",")]
             try:
@@ -187,7 +205,10 @@ def run_reference(args, wl, rank, world):
         "unit": "env-steps/s", "n_gpus": 0, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "board_size": size, "boards": cores * boards_per_core,
-                   "note": "CPU arm: a step = one ply on every board of the bounded sample"},
+                   "note": "CPU arm: a step = one ply on every board of the bounded sample; kind=port: the reference is "
+                           "pure Python with gym/pyglet imports and cannot travel to the GPU box; the port keeps its "
+                           "scipy.ndimage arithmetic and ran 1.35-1.5x faster than the unmodified reference in the "
+                           "build container (ratios against this arm are conservative)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -196,9 +217,95 @@ def run_reference(args, wl, rank, world):
 
 
 # ------------------------------------------------------------------------------- GPU arm
+def _events():
+    import torch
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+class RolloutBench(object):
+    """one (board size, batch) rollout workload on this rank's GPU: pre-rolled records + output buffers"""
+
+    def __init__(self, eng, boards, board0, obs_dtype, obs_elem, ppl, preroll=PREROLL):
+        import torch
+        self.eng, self.boards, self.board0, self.ppl = eng, boards, board0, ppl
+        self.obs_elem, n = obs_elem, eng.size
+        self.ring = eng.empty((ppl, boards, 6, n, n), dtype=obs_dtype)          # one slot per ply of a launch
+        self.actions = eng.empty((ppl, boards), dtype=torch.int32)
+        self.reward = eng.empty((ppl, boards), dtype=torch.float32)
+        self.done = eng.empty((ppl, boards))
+        self.rec = eng.new_records(boards)
+        self.t = 0
+        eng.rollout(self.rec, SEED, board0, 0, preroll, plies_per_launch=32)     # untimed set-up
+        self.t = preroll
+        self.ring_bytes = self.ring.numel() * obs_elem
+
+    def plies(self, count):
+        """`count` plies, all outputs, <= ppl plies per launch; -> launches"""
+        done, launches = 0, 0
+        while done < count:
+            n = min(self.ppl, count - done)
+            self.eng.rollout(self.rec, SEED, self.board0, self.t, n, plies_per_launch=n, actions_log=self.actions,
+                             obs_ring=self.ring, done_log=self.done, reward_log=self.reward, reward_mode=1, komi=0.0)
+            self.t += n
+            done += n
+            launches += 1
+        return launches
+
+    def timed(self, k, repeats):
+        import torch
+        ev0, ev1 = _events()
+        ev0.record()
+        launches = 0
+        for _ in range(repeats):
+            launches += self.plies(k)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / 1e3, launches
+
+
+def pick_repeats(trial_secs_all_ranks):
+    return max(1, int(-(-MIN_TIMED_MS / 1e3 // max(trial_secs_all_ranks, 1e-6))))
+
+
+def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches, peak, peak_src):
+    size = eng.size
+    bytes_per_ply = algorithmic_bytes_per_ply(size, obs_elem)
+    plies_in_launch = repeats * k / float(launches)                   # plies one launch really played
+    launch_s = secs / launches
+    per_launch = boards * bytes_per_ply * plies_in_launch
+    achieved = per_launch / launch_s / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": profiled_traffic(size, obs_name, plies_in_launch),
+            "algorithmic_bytes_per_launch": per_launch, "plies_per_launch": plies_in_launch,
+            "kernel": "gg::%s, Geo<%d>" % (eng.lib.gg_rollout_kernel(size, boards).decode(), size),
+            "bytes_per_ply": bytes_per_ply, "peak_source": peak_src, "launch_us": launch_s * 1e6,
+            "timing": "CUDA events on the launching stream around %d launches" % launches}
+
+
+def measure_children(eng, parents_n, board0, repeats=10):
+    """configs[3]: children(padded=True) of `parents_n` 9x9 boards after 40 random-legal plies (seed 0);
+    -> (seconds per call, bytes written per call)"""
+    import torch
+    parents = eng.new_records(parents_n)
+    eng.rollout(parents, SEED, board0, 0, 40, plies_per_launch=8)
+    eng.reset(parents, (eng.flags(parents) & 4) != 0)                  # a finished parent has no children: restart it
+    for _ in range(3):
+        out = eng.children(parents, obs_dtype=torch.float32, want_rec=True)
+    torch.cuda.synchronize()
+    ev0, ev1 = _events()
+    ev0.record()
+    for _ in range(repeats):
+        out = eng.children(parents, obs_dtype=torch.float32, want_rec=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    written = sum(out[k].numel() * out[k].element_size() for k in ("rec", "obs", "valid", "status"))
+    return ev0.elapsed_time(ev1) / 1e3 / repeats, written, repeats
+
+
 def run_ours(args, wl, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+    from gymgo_b200 import hostmem, sharding
     from gymgo_b200.engine import GoEngine
     from gymgo_b200.envs import BatchedGoEnv
 
@@ -206,179 +313,217 @@ def run_ours(args, wl, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    bound_cpus = hostmem.bind_thread_near(local_rank)                  # best effort; 0 = topology not visible
     size, boards = wl["size"], args.boards or wl["boards"]
     obs_dtype = {"f32": torch.float32, "u8": torch.uint8, "bf16": torch.bfloat16}[args.obs]
     obs_elem = {"f32": 4, "u8": 1, "bf16": 2}[args.obs]
     eng = GoEngine(size, dev)
     board0 = rank * boards
     K, W = args.steps, args.warmup
-
-    # rotating observation buffers: > L2 (126 MB) in total so no step rewrites lines still in cache
-    dense_bytes = boards * 6 * size * size * obs_elem
-    nbuf = max(2, int(-(-300e6 // dense_bytes)))
-    obs_ring = eng.empty((nbuf, boards, 6, size, size), dtype=obs_dtype)
-    rec = eng.new_records(boards)
-    # The e2e leg replays the first W + E plies of this very rollout from host memory, so their actions are
-    # recorded; later plies log into a reusable chunk (reward / done are always logged, like an RL loop needs).
-    E = min(K, 300) if args.e2e_steps is None else min(K, args.e2e_steps)
-    CHUNK = 256
-    actions_replay = torch.empty((W + E, boards), dtype=torch.int32, device=dev)
-    actions_chunk = torch.empty((CHUNK, boards), dtype=torch.int32, device=dev)
-    reward_chunk = torch.empty((CHUNK, boards), dtype=torch.float32, device=dev)
-    done_chunk = torch.empty((CHUNK, boards), dtype=torch.uint8, device=dev)
-    ppl = args.plies_per_launch
-
-    def plies(t0, count):
-        """gg_rollout (persistent kernel, `ppl` plies per launch, boards in registers) in calls of <= CHUNK plies"""
-        launches, t, end = 0, t0, t0 + count
-        while t < end:
-            n = min(CHUNK, end - t)
-            if t < W + E:
-                n = min(n, W + E - t)
-                alog = actions_replay[t:]
-            else:
-                alog = actions_chunk
-            eng.rollout(rec, SEED, board0, t, n, plies_per_launch=ppl, actions_log=alog, obs_ring=obs_ring,
-                        done_log=done_chunk, reward_log=reward_chunk, reward_mode=1, komi=0.0)
-            launches += -(-n // ppl)
-            t += n
-        return launches
+    ppl = max(1, min(args.plies_per_launch, K))
+    peak, peak_src = measured_peak_gbs()
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    plies(0, W)
-    barrier()
+    def gather(values):
+        return sharding.gather_counters(values, device=dev)
+
+    # ---------------- headline: device-resident rollout
+    main = RolloutBench(eng, boards, board0, obs_dtype, obs_elem, ppl)
+    main.plies(W)                                                      # warm-up (the argument)
+    trial, _ = main.timed(K, 1)                                        # untimed trial: sizes the repetition count
+    R = pick_repeats(float(gather([trial])[:, 0].max()))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        time.sleep(0.25)
     barrier()
     wall0 = time.time()
-    ev0.record()
-    n_launches = plies(W, K)
-    ev1.record()
+    secs, n_launches = main.timed(K, R)                                # THE timed region: R x K steps
     barrier()
     wall1 = time.time()
-    secs = ev0.elapsed_time(ev1) / 1e3
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    # reference state for the e2e replay check: the rollout after exactly W + E plies (deterministic re-run, untimed)
-    final_rec = eng.new_records(boards)
-    eng.rollout(final_rec, SEED, board0, 0, W + E, plies_per_launch=ppl)
 
-    # ---------------- transparency: the same plies with ONE launch per ply (no register residency across plies)
-    scratch = rec.clone()
-    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n1 = min(K, 100)
-    eng.rollout(scratch, SEED, board0, W + K, 8, plies_per_launch=1, obs_ring=obs_ring)
+    # ---------------- transparency: the same plies with ONE launch per ply (records reloaded and stored every ply)
+    n1 = min(max(K, 20), 100)
+    one = RolloutBench(eng, boards, board0, obs_dtype, obs_elem, 1, preroll=0)
+    one.rec.copy_(main.rec)
+    one.t = main.t
+    one.plies(8)
+    one_secs, _ = one.timed(n1, 1)
+    del one
+
+    # ---------------- e2e: the public host-buffer step (BatchedGoEnv.host_stepper), copies inside the timed region.
+    # The host plays the part of the policy by replaying the device rollout's own actions (recorded below), and the run
+    # refuses to report if the replayed boards do not end up identical to the device rollout's.
+    E = min(max(K, 20), 300) if args.e2e_steps is None else max(1, args.e2e_steps)
+    We = min(W, 20)
+    start_rec = main.rec.clone()
+    t_start = main.t
+    replay = torch.empty((We + E, boards), dtype=torch.int32, device=dev)
+    final_rec = start_rec.clone()
+    eng.rollout(final_rec, SEED, board0, t_start, We + E, plies_per_launch=32, actions_log=replay)
+    replay_host = torch.empty((We + E, boards), dtype=torch.int32, pin_memory=True)
+    replay_host.copy_(replay)
     torch.cuda.synchronize()
-    ev4.record()
-    eng.rollout(scratch, SEED, board0, W + K + 8, n1, plies_per_launch=1, obs_ring=obs_ring, done_log=done_chunk,
-                reward_log=reward_chunk, actions_log=actions_chunk, reward_mode=1, komi=0.0)
-    ev5.record()
-    torch.cuda.synchronize()
-    one_ply_secs = ev4.elapsed_time(ev5) / 1e3
+    del main
 
-    # ---------------- e2e: the public BatchedGoEnv.step with HOST buffers, copies inside the timed region
-    actions_host = torch.empty((W + E, boards), dtype=torch.int32, pin_memory=True)
-    actions_host.copy_(actions_replay)
-    env = BatchedGoEnv(boards, size, reward_method="real", device=dev, obs_dtype=obs_dtype, board_offset=board0)
-    obs_host = torch.empty((boards, 6, size, size), dtype=obs_dtype, pin_memory=True)
-    rew_host = torch.empty((boards,), dtype=torch.float32, pin_memory=True)
-    done_host = torch.empty((boards,), dtype=torch.uint8, pin_memory=True)
-    a_dev = env.action_buffer                                               # the env's static action tensor
+    def e2e_leg(returns, dtype, expand=False):
+        env = BatchedGoEnv(boards, size, reward_method="real", device=dev, obs_dtype=dtype, board_offset=board0)
+        env.rec.copy_(start_rec)
+        env.done.copy_(((eng.flags(start_rec) >> 2) & 1).to(torch.uint8))
+        hs = env.host_stepper(returns=returns, auto_reset=True, follow_current_stream=False)
+        dense = torch.empty((boards, 6, size, size), dtype=torch.float32) if expand else None
+        torch.cuda.synchronize()                                         # set-up above ran on the default stream
+        for t in range(We):
+            hs.actions.copy_(replay_host[t])
+            hs.step()
+        barrier()
+        ev0, ev1 = _events()
+        wall = time.time()
+        ev0.record()
+        for t in range(We, We + E):
+            hs.actions.copy_(replay_host[t])                              # the "policy": host memory -> pinned buffer
+            hs.step()                                                     # H2D, one kernel, D2H, wait
+            if expand:
+                hs.expand(out=dense)                                      # packed records -> f32 on the host cores
+        ev1.record()
+        torch.cuda.synchronize()
+        wall = time.time() - wall
+        barrier()
+        ok = torch.equal(env.rec, final_rec)
+        return dict(secs=ev0.elapsed_time(ev1) / 1e3, wall=wall, h2d=hs.h2d_bytes, d2h=hs.d2h_bytes, ok=ok,
+                    placement=hs.placement)
 
-    def e2e_ply(t):
-        a_dev.copy_(actions_host[t], non_blocking=True)                     # H2D: this step's actions
-        o, r, d, _ = env.step(a_dev, auto_reset=True)                       # reset finished boards + one ply
-        obs_host.copy_(o, non_blocking=True)                                # D2H: observation, reward, done
-        rew_host.copy_(r, non_blocking=True)
-        done_host.copy_(d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                           # the host now owns the result
-
-    e2e_steps = E
-    for t in range(W):
-        e2e_ply(t)
-    barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    for t in range(W, W + e2e_steps):
-        e2e_ply(t)
-    ev3.record()
-    barrier()
-    e2e_secs = ev2.elapsed_time(ev3) / 1e3
-    if not torch.equal(env.rec, final_rec):
+    legs = {"f32": e2e_leg("obs", obs_dtype)}
+    if not legs["f32"]["ok"]:
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
+    if not args.quick:
+        legs["u8"] = e2e_leg("obs", torch.uint8)
+        legs["packed"] = e2e_leg("packed", obs_dtype)
+        legs["packed_expanded"] = e2e_leg("packed", obs_dtype, expand=True)
+        legs["obs_kept_on_device"] = e2e_leg("none", obs_dtype)
+        for name, leg in legs.items():
+            if not leg["ok"]:
+                raise SystemExit("e2e variant %s diverged from the device rollout - refusing to report" % name)
 
-    # ---------------- informational: the same host-driven loop when the observation stays on the device (the
-    # consumer is a device-resident policy network): actions H2D, reward + done D2H, synchronised every step
-    env.reset()
+    # ---------------- the other BASELINE configs, measured in the same run (rank-local, gathered below)
+    extra_local = {}
+    if not args.quick:
+        other = "19x19" if args.workload == "9x9" else "9x9"
+        owl = WORKLOADS[other]
+        oeng = GoEngine(owl["size"], dev)
+        ob = RolloutBench(oeng, owl["boards"], rank * owl["boards"], torch.float32, 4, 32)
+        ob.plies(32)
+        ot, _ = ob.timed(32, 1)
+        oR = pick_repeats(float(gather([ot])[:, 0].max()))
+        barrier()
+        osecs, olaunches = ob.timed(32, oR)
+        barrier()
+        extra_local["rollout"] = (owl, oeng, osecs, oR, olaunches)
+        del ob
+        ceng = GoEngine(9, dev)
+        csecs, cbytes, creps = measure_children(ceng, 4096, rank * 4096)
+        extra_local["children"] = (csecs, cbytes, creps)
 
-    def e2e_ply_light(t):
-        a_dev.copy_(actions_host[t], non_blocking=True)
-        _, r, d, _ = env.step(a_dev, auto_reset=True)
-        rew_host.copy_(r, non_blocking=True)
-        done_host.copy_(d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    light_steps = min(e2e_steps, W + E)
-    torch.cuda.synchronize()
-    ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev6.record()
-    for t in range(light_steps):
-        e2e_ply_light(t)
-    ev7.record()
-    torch.cuda.synchronize()
-    light_secs = ev6.elapsed_time(ev7) / 1e3
-
-    # ---------------- gather (plies, seconds) of every rank: the only collective of the job
-    from gymgo_b200 import sharding
-    allr = sharding.gather_counters([float(boards) * K, secs, float(boards) * e2e_steps, e2e_secs], device=dev)
+    # ---------------- gather the counters of every rank (the only collectives of the job; none is timed)
+    vals = [float(boards) * K * R, secs, float(boards) * E, legs["f32"]["secs"]]
+    for name in ("u8", "packed", "packed_expanded", "obs_kept_on_device"):
+        vals.append(legs[name]["secs"] if name in legs else 0.0)
+    if extra_local:
+        owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
+        vals += [float(owl["boards"]) * 32 * oR, osecs, extra_local["children"][0]]
+    allr = gather(vals)
     if rank == 0:
         total_plies, t_max = float(allr[:, 0].sum()), float(allr[:, 1].max())
-        e2e_plies, e2e_t = float(allr[:, 2].sum()), float(allr[:, 3].max())
         value = total_plies / t_max
-        bytes_per_ply = algorithmic_bytes_per_ply(size, obs_elem)
-        peak, peak_src = measured_peak_gbs()
-        launch_s = float(allr[0, 1]) / n_launches                      # average duration of one kernel launch
-        achieved = boards * bytes_per_ply * (K / float(n_launches)) / launch_s / 1e9
+        e2e_plies = float(allr[:, 2].sum())
+
+        def e2e_value(col):
+            return e2e_plies / float(allr[:, col].max())
+
+        def leg_record(name, col, api):
+            leg = legs[name]
+            return {"value": e2e_value(col), "unit": "env-steps/s", "h2d_bytes_per_step": leg["h2d"] * world,
+                    "d2h_bytes_per_step": leg["d2h"] * world,
+                    "pcie_gbs_per_gpu": (leg["h2d"] + leg["d2h"]) * E / leg["secs"] / 1e9, "api": api}
+
+        e2e = leg_record("f32", 3, "BatchedGoEnv.host_stepper(returns='obs').step(): pinned-host int32 actions in; %s "
+                                   "observation + f32 reward + u8 done out to pinned host; H2D copy, ONE kernel "
+                                   "(gg_step with in-kernel auto-reset), D2H copies as one CUDA graph, waited for every "
+                                   "step" % args.obs)
+        e2e["steps"] = E
+        e2e["replay_check"] = "boards after the host-driven replay == device rollout (bit-exact)"
+        e2e["host_placement"] = dict(legs["f32"]["placement"], thread_bound_to_cpus=bound_cpus)
+        if not args.quick:
+            e2e["variants"] = {
+                "u8_observation": leg_record("u8", 4, "same call with obs_dtype=uint8"),
+                "packed_records": leg_record("packed", 5, "host_stepper(returns='packed'): the packed records instead of "
+                                                          "the dense observation"),
+                "packed_records_expanded_on_host": dict(
+                    leg_record("packed_expanded", 6, "returns='packed' + HostStepper.expand(): gg_host_unpack to f32 on "
+                                                     "the host cores inside the timed region"),
+                    host_threads=usable_cores()),
+                "obs_kept_on_device": leg_record("obs_kept_on_device", 7, "host_stepper(returns='none'): reward + done "
+                                                                          "only, observation consumed on the device"),
+            }
         line = {
             "metric": "env-steps/sec (batched random-legal rollout)", "value": value, "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_max / (K * R), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitboards" if size <= 9 else "u64 bitboards",
             "data": "synthetic",
             "config": {"workload": wl["name"], "board_size": size, "boards_per_gpu": boards,
-                       "global_boards": boards * world, "obs": args.obs, "policy": "uniform over valid actions incl. pass, "
-                       "Philox4x32-10 keyed (seed 0, global board, ply), auto-reset",
-                       "l2": "each step writes a %.0f MB observation (> L2) into one of %d rotating buffers; the "
-                             "%.1f MB packed state is L2-resident by nature" % (dense_bytes / 1e6, nbuf,
-                                                                               boards * eng.rec_bytes / 1e6),
-                       "plies_per_launch": args.plies_per_launch,
+                       "global_boards": boards * world, "obs": args.obs,
+                       "policy": "uniform over valid actions incl. pass, Philox4x32-10 keyed (seed 0, global board, "
+                                 "ply), auto-reset",
+                       "preroll_plies": PREROLL, "repeats": R,
+                       "timed_region": "%d repetitions x %d steps = %d plies per GPU (>= %.0f ms of device time), after "
+                                       "%d untimed set-up plies and %d warm-up steps" % (R, K, R * K, MIN_TIMED_MS,
+                                                                                        PREROLL, W),
+                       "l2": "every launch writes %d observations of %.0f MB into a %d-slot ring (%.1f GB >> 126 MB "
+                             "L2; all observations of a launch stay readable); the %.1f MB packed state is L2-resident "
+                             "by nature" % (ppl, boards * 6 * size * size * obs_elem / 1e6, ppl,
+                                            ppl * boards * 6 * size * size * obs_elem / 1e9,
+                                            boards * eng.rec_bytes / 1e6),
+                       "plies_per_launch": ppl,
                        "parallelism": "dp%d (independent boards, no data-path collective)" % world},
-            "e2e": {"value": e2e_plies / e2e_t, "unit": "env-steps/s",
-                    "h2d_bytes_per_step": boards * 4 * world,
-                    "d2h_bytes_per_step": (dense_bytes + boards * 5) * world, "steps": e2e_steps,
-                    "api": "BatchedGoEnv.step(actions, auto_reset=True): pinned-host actions in; %s observation, reward, "
-                           "done out to pinned host, stream-synchronised every step" % args.obs,
-                    "obs_kept_on_device": {"value": boards * light_steps * world / light_secs, "unit": "env-steps/s",
-                                           "d2h_bytes_per_step": boards * 5 * world,
-                                           "note": "rank-0 timing of the same loop when only reward + done go back to "
-                                                   "the host (observation consumed on the device); informational"}},
+            "e2e": e2e,
             "gpu_launches": n_launches,
-            "one_launch_per_ply": {"value": boards * n1 * world / one_ply_secs, "ms_per_step": 1e3 * one_ply_secs / n1,
+            "one_launch_per_ply": {"value": boards * n1 * world / one_secs, "ms_per_step": 1e3 * one_secs / n1,
                                    "note": "rank-0 timing of the same kernel with plies_per_launch=1 (records reloaded "
                                            "and stored every ply)"},
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(args.workload, args.obs, args.plies_per_launch),
-                         "algorithmic_bytes_per_launch": boards * bytes_per_ply * args.plies_per_launch, "kernel": "gg::%s, Geo<%d>, %d plies per launch" % (eng.lib.gg_rollout_kernel(size, boards).decode(), size,
-                                                                              args.plies_per_launch),
-                         "bytes_per_ply": bytes_per_ply, "peak_source": peak_src,
-                         "launch_us": launch_s * 1e6},
+            "roofline": roofline_record(eng, boards, obs_elem, args.obs, K, float(allr[0, 1]), R, n_launches, peak,
+                                        peak_src),
         }
+        if extra_local:
+            owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
+            o_plies, o_t = float(allr[:, 8].sum()), float(allr[:, 9].max())
+            c_t = float(allr[:, 10].max())
+            csecs, cbytes, creps = extra_local["children"]
+            line["extra"] = {
+                "rollout_" + ("19x19" if owl["size"] == 19 else "9x9"): {
+                    "workload": owl["name"] + (" per GPU; x%d GPUs = %d boards%s" % (
+                        world, owl["boards"] * world, " = configs[4]" if owl["size"] == 19 and world == 8 else "")
+                        if world > 1 else ""),
+                    "value": o_plies / o_t, "unit": "env-steps/s", "ms_per_step": 1e3 * o_t / (32 * oR),
+                    "steps": 32 * oR, "preroll_plies": PREROLL, "obs": "f32",
+                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", 32, float(allr[0, 9]), oR, olaunches,
+                                                peak, peak_src)},
+                "children_9x9": {
+                    "workload": "gogame.children(padded=True) of 4,096 9x9 parents%s after 40 random-legal plies (seed 0): "
+                                "82 child slots per parent, packed records + f32 dense states + valid mask "
+                                "(configs[3])" % (" per GPU" if world > 1 else ""),
+                    "parent_expansions_per_s": 4096 * world / c_t, "child_states_per_s": 4096 * 82 * world / c_t,
+                    "us_per_call": c_t * 1e6, "calls_timed": creps,
+                    "roofline": {"bound": "hbm", "achieved": cbytes / csecs / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": cbytes / csecs / 1e9 / peak, "traffic": None,
+                                 "algorithmic_bytes_per_launch": cbytes, "kernel": "gg::k_step<Geo<9>, CHILDREN>",
+                                 "peak_source": peak_src}},
+            }
         if world == 1 and not args.no_cpu_baseline:
             # the CPU arm runs in a fresh interpreter (no CUDA context / torch thread pools to fork)
             env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
@@ -399,8 +544,8 @@ def run_ours(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10000,
-                    help="timed plies (default 10,000 = about a quarter second per GPU, long enough to sample clocks)")
+    ap.add_argument("--steps", type=int, default=2000, help="timed steps per repetition (the region is repeated until it "
+                                                             "lasts >= %d ms)" % MIN_TIMED_MS)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="9x9", choices=sorted(WORKLOADS))
@@ -410,9 +555,12 @@ def main():
     ap.add_argument("--plies-per-launch", type=int, default=32,
                     help="plies the persistent rollout kernel plays per launch (boards stay in registers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + f32 e2e only (no extra configs, no e2e variants)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.steps < 1:
+        args.steps = 1
     if args.impl == "ours" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself as one process per GPU (what the driver does)
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",

@@ -14,7 +14,7 @@ GG_OK, GG_EINVAL, GG_ESIZE, GG_EALIGN, GG_ECUDA = 0, -1, -2, -3, -4
 GG_ST_OK, GG_ST_INVALID_MOVE, GG_ST_OUT_OF_RANGE, GG_ST_GAME_OVER = 0, 1, 2, 3
 GG_U8, GG_F32, GG_F64, GG_BF16, GG_F16 = 0, 1, 2, 3, 4
 GG_STEP_CANONICAL, GG_STEP_REFUSE_DONE, GG_STEP_AUTO_RESET, GG_STEP_RESET_SKIPS_ACTION = 1, 2, 4, 8
-GG_KERNEL_AUTO, GG_KERNEL_LANES, GG_KERNEL_THREAD, GG_KERNEL_LANES_WS = -1, 0, 1, 2
+GG_KERNEL_AUTO, GG_KERNEL_LANES, GG_KERNEL_THREAD = -1, 0, 1
 GG_VERSION = 200
 
 GG_REWARD_NONE, GG_REWARD_REAL, GG_REWARD_HEURISTIC = 0, 1, 2

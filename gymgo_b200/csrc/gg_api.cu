@@ -29,7 +29,7 @@ static const SizeVTable* lookup(int n) {
 static thread_local char g_err[256] = "";
 
 // Which persistent rollout kernel serves (n, batch) when the caller asks for GG_KERNEL_AUTO.  Measured on the B200
-// with f32 observations (profiles/r01_variant_threshold.json, profiles/r02_kernel_ab.json): all kernels sit within a
+// with f32 observations (profiles/r01_variant_threshold.json, profiles/r02_kernel_ab.json): both kernels sit within a
 // few percent of the pure-write floor on small boards; thread-per-board is ahead by up to 5 % on small boards around
 // 64 Ki boards, behind below 32 Ki (too few warps) and level at 128 Ki (write-bound either way).
 static int auto_kernel(const SizeVTable* v, int64_t batch) {
@@ -38,9 +38,7 @@ static int auto_kernel(const SizeVTable* v, int64_t batch) {
     return GG_KERNEL_LANES;
 }
 static const char* kernel_name(int k) {
-    return k == GG_KERNEL_THREAD ? "k_rollout_tpb (thread per board)"
-                                 : (k == GG_KERNEL_LANES_WS ? "k_rollout_ws (lane-sliced boards, emitter warps)"
-                                                            : "k_rollout (lane-sliced boards)");
+    return k == GG_KERNEL_THREAD ? "k_rollout_tpb (thread per board)" : "k_rollout (lane-sliced boards)";
 }
 
 static int finish(cudaError_t e) {
@@ -205,7 +203,7 @@ GG_API int gg_rollout_with(int kernel, void* rec, int64_t batch, int n, uint64_t
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
     if (batch < 0 || steps < 0 || plies_per_launch < 1 || (batch > 0 && !rec)) return GG_EINVAL;
-    if (kernel < GG_KERNEL_AUTO || kernel > GG_KERNEL_LANES_WS) return GG_EINVAL;
+    if (kernel < GG_KERNEL_AUTO || kernel > GG_KERNEL_THREAD) return GG_EINVAL;
     if (obs_ring_buf && (!dense_dtype_ok(obs_dtype, false) || obs_ring < 1)) return GG_EINVAL;
     if (reward_mode < GG_REWARD_NONE || reward_mode > GG_REWARD_HEURISTIC) return GG_EINVAL;
     if (!aligned16(rec) || !aligned16(obs_ring_buf)) return GG_EALIGN;
@@ -246,7 +244,7 @@ GG_API const char* gg_rollout_kernel(int n, int64_t batch) {
 }
 
 GG_API const char* gg_kernel_name(int kernel) {
-    return (kernel >= GG_KERNEL_LANES && kernel <= GG_KERNEL_LANES_WS) ? kernel_name(kernel) : "";
+    return (kernel >= GG_KERNEL_LANES && kernel <= GG_KERNEL_THREAD) ? kernel_name(kernel) : "";
 }
 
 GG_API int gg_update_pieces(void* rec, const void* touch, const int32_t* player, void* killed, int64_t batch, int n, void* stream) {

@@ -65,9 +65,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {    // release at CTA scope (PTX default)
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -555,8 +552,7 @@ struct RolloutArgs {
     float komi;
     void* obs_ring;             // [ring, B, 6, N, N] or NULL; ply t writes slot t % ring
     int obs_dtype, ring;
-    int variant;                // 0: k_rollout (lane-sliced boards), 1: k_rollout_tpb (thread per board),
-                                // 2: k_rollout_ws (lane-sliced boards, observation emission by dedicated warps)
+    int variant;                // 0: k_rollout (lane-sliced boards), 1: k_rollout_tpb (thread per board)
 };
 
 template <class G>
@@ -570,6 +566,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     typedef typename G::W W;
     typedef Tile<G> T;
     typedef WarpStream<G> WS;
+    typedef DevOps<G> O;
     __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
     __shared__ uint32_t s_bits_all[T::WPC][WS::W32];
     __shared__ __align__(16) float4 s_lut[LUT_F4];
@@ -580,7 +577,6 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     const long long left = a.boards - tile_base;
     const int nb = left < T::BT ? int(left) : T::BT;
     const bool want_obs = a.obs_ring != nullptr;
-    uint32_t* s_bits = s_bits_all[warp];
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -598,7 +594,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     const int slot_local = warp * G::BPW + slot_in_warp;
     const bool real = slot_in_warp < G::BPW && slot_local < nb;
     const long long slot = tile_base + slot_local;
-    DevOps<G> o;
+    O o;
     o.init(lane, real);
     const int j = o.j;
     const bool holder = real && G::rows_in_lane(j) > 0;
@@ -631,8 +627,8 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
         }
         const uint32_t rnd = philox4x32_10(uint32_t(gb), uint32_t(gb >> 32), uint32_t(t), uint32_t(t >> 32),
                                            uint32_t(a.seed), uint32_t(a.seed >> 32));
-        const int action = Algo<DevOps<G>>::sample_action(o, G(), invd, rnd);
-        Algo<DevOps<G>>::step(o, G(), black, white, invd, flags, action, 0u);
+        const int action = Algo<O>::sample_action(o, G(), invd, rnd);
+        Algo<O>::step(o, G(), black, white, invd, flags, action, 0u);
 
         const bool over = (flags & FLAG_DONE) != 0;
         const long long log_at = (long long)p * a.boards + slot;
@@ -645,7 +641,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
             float r = 0.f;
             if (need_areas) {
                 int ba, wa;
-                Algo<DevOps<G>>::areas(o, black, white, ba, wa);
+                Algo<O>::areas(o, black, white, ba, wa);
                 const float diff = float(ba - wa) - a.komi;
                 if (a.reward_mode == 1) r = over ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
                 else r = over ? (diff > 0.f ? float(G::NP) : -float(G::NP)) : diff;
@@ -657,6 +653,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
             const long long abs0 = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0;
             const int head = int(abs0 & align_mask);
             const long long at = abs0 - head;
+            uint32_t* s_bits = s_bits_all[warp];
             for (int i = lane; i < WS::W32; i += 32) s_bits[i] = 0;
             __syncwarp();
             if (holder) stream_put_board<G>(s_bits, head + slot_in_warp * WS::DENSE, j, black, white, invd, flags);
@@ -674,169 +671,6 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     }
     if (real && j == 0) my_rec[G::FLAGS_IDX] = flags;
     fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-        bulk_s2g(a.rec + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
-        bulk_commit_wait_all();
-    }
-}
-
-// =================================================================================================
-// Warp-specialised persistent rollout kernel.  Same board layout, rules and outputs as k_rollout, but the dense
-// observation is written by DEDICATED emitter warps: a rule warp only drops its boards' bits into one of two
-// stream buffers in shared memory and signals an mbarrier; the emitter expands the buffer to 16-byte stores while
-// the rule warp is already playing the next ply.  The rule warps' dependency chains (shuffles, votes, carry chains)
-// no longer contain the store loop, and the emitter warps - independent, memory-stall tolerant instruction streams -
-// fill the issue slots the latency-bound rule warps leave empty.
-//   full[w][b]  : rule warp w -> emitter   "buffer b holds ply p"       (one arrival per use)
-//   empty[w][b] : emitter -> rule warp w   "buffer b is zeroed again"   (one arrival per use)
-// =================================================================================================
-template <class G>
-struct WsTile {
-    static constexpr int RW = Tile<G>::WPC;                        // rule warps per CTA
-    static constexpr int EW = G::WB == 32 ? 2 : 1;                 // emitter warps per CTA (each serves RW / EW rule warps)
-    static constexpr int THREADS = (RW + EW) * 32;
-    static constexpr int BT = RW * G::BPW;
-    static constexpr int NBUF = 2;
-    static constexpr int WANT_BLOCKS = G::WB == 32 ? 8 : 7;         // 19x19 x 16,384: 6.9 CTAs per SM, all resident
-    static constexpr int MIN_BLOCKS = WANT_BLOCKS * THREADS <= 2048 ? WANT_BLOCKS : 2048 / THREADS;
-    static_assert(RW % EW == 0, "every emitter serves the same number of rule warps");
-};
-
-template <class G>
-__global__ void __launch_bounds__(WsTile<G>::THREADS, WsTile<G>::MIN_BLOCKS) k_rollout_ws(const RolloutArgs a) {
-    typedef typename G::W W;
-    typedef WsTile<G> T;
-    typedef WarpStream<G> WS;
-    __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
-    __shared__ uint32_t s_bits_all[T::RW][T::NBUF][WS::W32];
-    __shared__ __align__(16) float4 s_lut[LUT_F4];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(8) uint64_t s_full[T::RW][T::NBUF];
-    __shared__ __align__(8) uint64_t s_empty[T::RW][T::NBUF];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile_base = (long long)blockIdx.x * T::BT;
-    const long long left = a.boards - tile_base;
-    const int nb = left < T::BT ? int(left) : T::BT;
-    const bool want_obs = a.obs_ring != nullptr;
-
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        for (int w = 0; w < T::RW; ++w)
-            for (int b = 0; b < T::NBUF; ++b) {
-                mbar_init(&s_full[w][b], 1);
-                mbar_init(&s_empty[w][b], 1);
-            }
-        fence_mbar_init();
-    }
-    obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
-    for (int i = tid; i < T::RW * T::NBUF * WS::W32; i += T::THREADS) (&s_bits_all[0][0][0])[i] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
-        bulk_g2s(s_rec, a.rec + tile_base * G::REC_W32, uint32_t(nb) * G::REC_BYTES, &s_bar);
-    }
-
-    const int align_mask = obs_align_mask(a.obs_dtype);            // elements per 16-byte vector, minus 1
-    const long long slot_elems = a.boards * WS::DENSE;
-
-    if (warp >= T::RW) {
-        // ------------------------------------------------------------------ emitter warp
-        if (want_obs) {
-            for (int p = 0; p < a.plies; ++p) {
-                const unsigned long long t = a.t0 + (unsigned long long)p;
-                const int buf = p % T::NBUF, use = p / T::NBUF;
-                const long long slot0 = (long long)(t % (unsigned long long)a.ring) * slot_elems;
-                for (int w = warp - T::RW; w < T::RW; w += T::EW) {
-                    int nbw = nb - w * G::BPW;
-                    nbw = nbw < 0 ? 0 : (nbw > G::BPW ? G::BPW : nbw);
-                    const long long abs0 = slot0 + (tile_base + w * G::BPW) * WS::DENSE;
-                    const int head = int(abs0 & align_mask);
-                    uint32_t* s_bits = s_bits_all[w][buf];
-                    mbar_wait(&s_full[w][buf], uint32_t(use & 1));
-                    emit_obs<32>(a.obs_dtype, s_bits, s_lut, head, nbw * WS::DENSE, a.obs_ring, abs0 - head, lane);
-                    __syncwarp();
-                    for (int i = lane; i < WS::W32; i += 32) s_bits[i] = 0;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_empty[w][buf]);
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ rule warp
-        mbar_wait(&s_bar, 0);
-        const int slot_in_warp = lane / G::LPB;
-        const int slot_local = warp * G::BPW + slot_in_warp;
-        const bool real = slot_in_warp < G::BPW && slot_local < nb;
-        const long long slot = tile_base + slot_local;
-        DevOps<G> o;
-        o.init(lane, real);
-        const int j = o.j;
-        const bool holder = real && G::rows_in_lane(j) > 0;
-        uint32_t* my_rec = s_rec + slot_local * G::REC_W32;
-
-        W black = 0, white = 0, invd = 0;
-        uint32_t flags = 0;
-        if (holder) {
-            black = rec_word<G>(my_rec, 0, j);
-            white = rec_word<G>(my_rec, 1, j);
-            invd = rec_word<G>(my_rec, 2, j);
-        }
-        if (real) flags = my_rec[G::FLAGS_IDX];
-        const long long e0 = (tile_base + warp * G::BPW) * WS::DENSE;
-        const unsigned long long gb = a.board0 + (unsigned long long)slot;
-
-        for (int p = 0; p < a.plies; ++p) {
-            const unsigned long long t = a.t0 + (unsigned long long)p;
-            if (flags & FLAG_DONE) {                                   // auto-reset (gogame.init_state)
-                black = white = invd = 0;
-                flags = 0;
-            }
-            const uint32_t rnd = philox4x32_10(uint32_t(gb), uint32_t(gb >> 32), uint32_t(t), uint32_t(t >> 32),
-                                               uint32_t(a.seed), uint32_t(a.seed >> 32));
-            const int action = Algo<DevOps<G>>::sample_action(o, G(), invd, rnd);
-            Algo<DevOps<G>>::step(o, G(), black, white, invd, flags, action, 0u);
-
-            const bool over = (flags & FLAG_DONE) != 0;
-            const long long log_at = (long long)p * a.boards + slot;
-            if (real && j == 0) {
-                if (a.actions_log) a.actions_log[log_at] = action;
-                if (a.done_log) a.done_log[log_at] = over ? 1 : 0;
-            }
-            if (a.reward_log) {
-                const bool need_areas = a.reward_mode == 2 || __any_sync(0xffffffffu, over);
-                float r = 0.f;
-                if (need_areas) {
-                    int ba, wa;
-                    Algo<DevOps<G>>::areas(o, black, white, ba, wa);
-                    const float diff = float(ba - wa) - a.komi;
-                    if (a.reward_mode == 1) r = over ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
-                    else r = over ? (diff > 0.f ? float(G::NP) : -float(G::NP)) : diff;
-                }
-                if (real && j == 0) a.reward_log[log_at] = r;
-            }
-            if (want_obs) {
-                const int buf = p % T::NBUF, use = p / T::NBUF;
-                const long long abs0 = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0;
-                const int head = int(abs0 & align_mask);
-                if (use > 0) mbar_wait(&s_empty[warp][buf], uint32_t((use - 1) & 1));
-                if (holder)
-                    stream_put_board<G>(s_bits_all[warp][buf], head + slot_in_warp * WS::DENSE, j, black, white, invd, flags);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_full[warp][buf]);
-            }
-        }
-
-        __syncwarp();                                                  // flags word: reads (all lanes) before the write
-        if (holder) {
-            rec_word_store<G>(my_rec, 0, j, black);
-            rec_word_store<G>(my_rec, 1, j, white);
-            rec_word_store<G>(my_rec, 2, j, invd);
-        }
-        if (real && j == 0) my_rec[G::FLAGS_IDX] = flags;
-        fence_proxy_async();
-    }
     __syncthreads();
     if (tid == 0) {
         bulk_s2g(a.rec + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
@@ -1233,7 +1067,6 @@ struct SizeVTable {
     cudaError_t (*canonical)(const uint32_t*, uint32_t*, long long, cudaStream_t);
     cudaError_t (*symmetry)(const uint32_t*, uint32_t*, long long, int, cudaStream_t);
     cudaError_t (*capture)(uint32_t*, const uint32_t*, const int32_t*, uint32_t*, long long, cudaStream_t);
-    int ws_tile_boards, ws_tile_threads;
 };
 
 template <class G>
@@ -1249,7 +1082,6 @@ struct Launch {
     static cudaError_t rollout(const RolloutArgs& a, cudaStream_t s) {
         if (a.boards <= 0 || a.plies <= 0) return cudaSuccess;
         if (a.variant == 1) LaunchTpb<G>::go(a, s);
-        else if (a.variant == 2) k_rollout_ws<G><<<blocks_for(a.boards, WsTile<G>::BT), WsTile<G>::THREADS, 0, s>>>(a);
         else k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
         return cudaGetLastError();
     }
@@ -1317,8 +1149,7 @@ struct Launch {
     }
     static constexpr SizeVTable table() {
         return SizeVTable{G::N, G::REC_BYTES, G::LPB, G::RPL, G::WB, G::BPW, Tile<G>::BT, Tile<G>::THREADS,
-                          &step, &rollout, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical, &symmetry, &capture,
-                          WsTile<G>::BT, WsTile<G>::THREADS};
+                          &step, &rollout, &areas, &sample, &pack, &unpack, &valid, &reset, &canonical, &symmetry, &capture};
     }
 };
 

@@ -113,9 +113,10 @@ class BatchedGoEnv(object):
                                   "status %d" % int(self.status[i])))
         return self.obs, self.reward, self.done, {"status": self.status}
 
-    def host_stepper(self, returns="obs", auto_reset=True, use_cuda_graph=True):
+    def host_stepper(self, returns="obs", auto_reset=True, use_cuda_graph=True, follow_current_stream=True):
         """-> HostStepper: the step with HOST buffers (pinned actions in, pinned results out); see the class"""
-        return HostStepper(self, returns=returns, auto_reset=auto_reset, use_cuda_graph=use_cuda_graph)
+        return HostStepper(self, returns=returns, auto_reset=auto_reset, use_cuda_graph=use_cuda_graph,
+                           follow_current_stream=follow_current_stream)
 
     def random_step(self):
         """fused: auto-reset finished boards, draw a uniformly random legal action (incl. pass), play it.
@@ -181,9 +182,11 @@ class HostStepper(object):
              "packed" the packed records [B, rec_bytes] (40x fewer bytes than f32 on 9x9); hs.expand() unpacks them on
                       the host (gg_host_unpack, multi-threaded C++)
              "none"   reward and done only (the observation is consumed on the device)
-    reward (f32 [B]) and done (u8 [B]) always come back, in one copy."""
+    reward (f32 [B]) and done (u8 [B]) always come back, in one copy.
+    The step runs on the stepper's own stream; with follow_current_stream (default) it first waits for the work already
+    enqueued on torch's current stream (e.g. an env.reset()), so mixing it with the device API is safe."""
 
-    def __init__(self, env, returns="obs", auto_reset=True, use_cuda_graph=True):
+    def __init__(self, env, returns="obs", auto_reset=True, use_cuda_graph=True, follow_current_stream=True):
         if returns not in ("obs", "packed", "none"):
             raise ValueError("returns must be 'obs', 'packed' or 'none'")
         self.env, self.returns, self.auto_reset = env, returns, bool(auto_reset)
@@ -200,6 +203,7 @@ class HostStepper(object):
         self.d2h_bytes = self._tail.numel() + (self.obs.numel() * self.obs.element_size() if self.obs is not None else 0) \
             + (self.rec.numel() if self.rec is not None else 0)
         self._stream = torch.cuda.Stream(device=env.engine.device)
+        self.follow_current_stream = bool(follow_current_stream)
         self._graph = None
         self.use_cuda_graph = bool(use_cuda_graph)
         self.placement = hostmem.describe(dev)
@@ -217,6 +221,8 @@ class HostStepper(object):
     def step(self):
         env = self.env
         env.engine._enter()
+        if self.follow_current_stream:
+            self._stream.wait_stream(torch.cuda.current_stream(env.engine.device))
         with torch.cuda.stream(self._stream):
             if self.use_cuda_graph:
                 if self._graph is None:

@@ -75,11 +75,10 @@ extern "C" {
 #define GG_STEP_RESET_SKIPS_ACTION 8u /* with GG_STEP_AUTO_RESET: a board that was just reset does NOT play its action
                                        * this ply (status OK, empty board out) - gymnasium's next-step autoreset */
 
-/* rollout kernels (gg_rollout_with); all three produce identical results */
+/* rollout kernels (gg_rollout_with); both produce identical results */
 #define GG_KERNEL_AUTO (-1)    /* chosen per (n, batch) from measurements: what gg_rollout uses */
 #define GG_KERNEL_LANES 0      /* k_rollout: a board spread over adjacent lanes of a warp */
 #define GG_KERNEL_THREAD 1     /* k_rollout_tpb: one board per thread */
-#define GG_KERNEL_LANES_WS 2   /* k_rollout_ws: lane-sliced boards, observations written by dedicated emitter warps */
 
 GG_API int gg_version(void);
 GG_API const char *gg_last_cuda_error(void);

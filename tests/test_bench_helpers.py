@@ -21,10 +21,23 @@ def test_algorithmic_bytes_match_survey():
 def test_peak_and_traffic_lookups():
     peak, src = bench.measured_peak_gbs()
     assert 3000 < peak < 9000 and ("measured" in src or "fallback" in src)
-    t = bench.profiled_traffic("9x9", "f32", 32)
-    assert t is None or 3e9 < t < 5e9
-    assert bench.profiled_traffic("9x9", "f32", 7) is None
+    t = bench.profiled_traffic(9, "f32", 32)
+    assert t is None or (3e9 < t["dram_bytes_per_launch"] < 5e9 and "profiles/" in t["source"])
+    t20 = bench.profiled_traffic(9, "f32", 20)              # scaled to the plies a launch really plays
+    assert (t is None) == (t20 is None)
+    if t is not None:
+        assert abs(t20["dram_bytes_per_launch"] * 32 - t["dram_bytes_per_launch"] * 20) <= 64
+    assert bench.profiled_traffic(9, "f64", 32) is None
     assert 1 <= bench.usable_cores() <= (os.cpu_count() or 1)
+
+
+def test_repetition_count_covers_the_minimum_timed_region():
+    """a short driver run (e.g. --steps 20 = 0.5 ms of device time) is repeated until the timed region is long enough to
+    be representative; a long one is not repeated"""
+    assert bench.pick_repeats(0.0005) * 0.0005 >= bench.MIN_TIMED_MS / 1e3
+    assert bench.pick_repeats(0.0005) <= 125
+    assert bench.pick_repeats(0.25) == 1 and bench.pick_repeats(10.0) == 1
+    assert bench.PREROLL >= 200
 
 
 def test_reference_arm_json_contract():

@@ -47,7 +47,7 @@ def test_rollout_kernel_choice_and_new_argument_checks():
     from gymgo_b200 import _cabi
     lib = _cabi.lib()
     assert lib.gg_kernel_name(_cabi.GG_KERNEL_THREAD).decode().startswith("k_rollout_tpb")
-    assert lib.gg_kernel_name(_cabi.GG_KERNEL_LANES_WS).decode().startswith("k_rollout_ws")
+    assert lib.gg_kernel_name(_cabi.GG_KERNEL_LANES).decode().startswith("k_rollout (")
     assert lib.gg_kernel_name(7) == b""
     assert lib.gg_rollout_kernel(9, 65536).decode().startswith("k_rollout_tpb")      # configs[1]
     assert "tpb" not in lib.gg_rollout_kernel(19, 16384).decode()                      # configs[2]

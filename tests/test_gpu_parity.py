@@ -182,12 +182,12 @@ def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
 @pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 141), (13, 97), (16, 33), (2, 50)))
 @pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.float16))
 def test_rollout_kernels_are_bit_identical(eng, n, boards, dtype):
-    """the three persistent rollout kernels - lane-sliced, thread-per-board, lane-sliced with emitter warps - produce
-    the same records, observations and logs (gg_rollout_with forces each)"""
+    """the two persistent rollout kernels - lane-sliced and thread-per-board - produce the same records, observations
+    and logs (gg_rollout_with forces each)"""
     from gymgo_b200 import _cabi
     e = eng(n)
     outs = []
-    for kernel in (_cabi.GG_KERNEL_LANES, _cabi.GG_KERNEL_THREAD, _cabi.GG_KERNEL_LANES_WS):
+    for kernel in (_cabi.GG_KERNEL_LANES, _cabi.GG_KERNEL_THREAD):
         rec = e.new_records(boards)
         ring = e.empty((23, boards, 6, n, n), dtype=dtype)
         ring.fill_(3)
@@ -204,18 +204,18 @@ def test_rollout_kernels_are_bit_identical(eng, n, boards, dtype):
             assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("kernel", (0, 1))
 @pytest.mark.parametrize("n,boards,ppl,ring", ((19, 1000, 7, 3), (19, 64, 32, 32), (13, 500, 5, 2), (9, 2000, 9, 4), (6, 77, 3, 1)))
-def test_emitter_warp_kernel_long_launches(eng, n, boards, ppl, ring):
-    """k_rollout_ws with many plies per launch and small observation rings (buffer hand-over between rule and emitter
-    warps wraps around many times): every ring slot equals the observation the single-ply kernel writes"""
-    from gymgo_b200 import _cabi
+def test_rollout_small_rings_keep_the_last_ply(eng, n, boards, ppl, ring, kernel):
+    """many plies per launch into rings smaller than a launch: every ring slot ends up holding the observation of the
+    LAST ply mapped to it (what the single-ply kernel writes), for both persistent kernels"""
     e = eng(n)
     a, b = e.new_records(boards), e.new_records(boards)
     obs_ring = e.empty((ring, boards, 6, n, n), dtype=torch.float32)
     one = e.empty((boards, 6, n, n), dtype=torch.float32)
     t = 0
     for launch in range(6):
-        e.rollout(a, 11, 5, t, ppl, plies_per_launch=ppl, obs_ring=obs_ring, kernel=_cabi.GG_KERNEL_LANES_WS)
+        e.rollout(a, 11, 5, t, ppl, plies_per_launch=ppl, obs_ring=obs_ring, kernel=kernel)
         last = {}
         for p in range(ppl):
             e.rollout_step(b, 11, 5, t + p, obs=one)

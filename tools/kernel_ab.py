@@ -1,4 +1,4 @@
-"""Developer probe (GPU box): the three persistent rollout kernels side by side.
+"""Developer probe (GPU box): the two persistent rollout kernels side by side.
 
     python tools/kernel_ab.py [--out gpurun_out/kernel_ab.json] [--quick]
 
@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from gymgo_b200 import _cabi  # noqa: E402
 from gymgo_b200.engine import GoEngine  # noqa: E402
 
-NAMES = {0: "lanes", 1: "thread", 2: "lanes_ws"}
+NAMES = {0: "lanes", 1: "thread"}
 
 
 def bytes_per_ply(n, elem):
@@ -36,7 +36,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:  # noqa: BLE001
         peak = 6650.0
-    cases = [(9, 65536), (19, 16384), (13, 32768), (7, 65536), (9, 16384), (9, 131072), (19, 4096), (19, 65536)]
+    cases = [(9, 65536), (19, 16384), (13, 32768), (7, 65536), (9, 16384), (9, 32768), (9, 131072), (19, 4096), (19, 65536), (5, 131072), (11, 32768), (15, 16384)]
     if args.quick:
         cases = cases[:2]
     dtypes = (("f32", torch.float32, 4), ("u8", torch.uint8, 1), ("bf16", torch.bfloat16, 2), ("none", None, 0))
@@ -48,7 +48,7 @@ def main():
         for dname, dt, elem in dtypes:
             ring = None if dt is None else e.empty((args.ppl, boards, 6, n, n), dtype=dt)
             row = {"size": n, "boards": boards, "obs": dname}
-            for k in (0, 1, 2):
+            for k in (0, 1):
                 if k == 1 and n > 9 and boards * n * n > 16384 * 361 // 2 and dname != "f32":
                     continue                                    # thread-per-board on big boards: slow, sample f32 only
                 rec = start.clone()

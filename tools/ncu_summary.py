@@ -36,6 +36,12 @@ else:
             "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+    # pipe utilisation and the stall breakdown (which resource bounds the issue rate)
+    extra = [c for c in h if ("pipe_" in c and "pct_of_peak" in c) or c.startswith("smsp__average_warps_issue_stalled")
+             or c.startswith("smsp__average_warp_latency_issue_stalled") or c.startswith("smsp__warps_eligible")
+             or c.startswith("smsp__issue_inst0") or c.startswith("smsp__inst_executed_pipe")
+             or c.startswith("sm__inst_executed_pipe")]
+    want = want + sorted(extra)
     for r in rows[2:]:
         print("kernel:", r[h.index("Kernel Name")])
         for w in want:
