@@ -47,7 +47,7 @@ WORKLOADS = {
 }
 SEED = 0
 PREROLL = 256            # untimed set-up plies (>= the 200 SURVEY.md 8d asks for)
-MIN_TIMED_MS = 60.0      # the timed region is repeated until it lasts at least this long
+MIN_TIMED_MS = 250.0     # the timed region is repeated until it lasts at least this long (>= 20 clock samples)
 
 
 def algorithmic_bytes_per_ply(n, obs_bytes_per_elem):
@@ -398,6 +398,23 @@ def run_ours(args, wl, rank, world, local_rank):
         return dict(secs=ev0.elapsed_time(ev1) / 1e3, wall=wall, h2d=hs.h2d_bytes, d2h=hs.d2h_bytes, ok=ok,
                     placement=hs.placement)
 
+    def device_policy_leg():
+        """BatchedGoEnv.step driven from Python with the actions already on the device (a device-resident policy):
+        no host copies, launches pipeline, one synchronisation at the end"""
+        env = BatchedGoEnv(boards, size, reward_method="real", device=dev, obs_dtype=obs_dtype, board_offset=board0)
+        env.rec.copy_(start_rec)
+        for t in range(We):
+            env.step(replay[t], auto_reset=True)
+        barrier()
+        ev0, ev1 = _events()
+        ev0.record()
+        for t in range(We, We + E):
+            env.step(replay[t], auto_reset=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return dict(secs=ev0.elapsed_time(ev1) / 1e3, h2d=0, d2h=0, ok=torch.equal(env.rec, final_rec), placement=None)
+
     legs = {"f32": e2e_leg("obs", obs_dtype)}
     if not legs["f32"]["ok"]:
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
@@ -406,6 +423,7 @@ def run_ours(args, wl, rank, world, local_rank):
         legs["packed"] = e2e_leg("packed", obs_dtype)
         legs["packed_expanded"] = e2e_leg("packed", obs_dtype, expand=True)
         legs["obs_kept_on_device"] = e2e_leg("none", obs_dtype)
+        legs["device_policy"] = device_policy_leg()
         for name, leg in legs.items():
             if not leg["ok"]:
                 raise SystemExit("e2e variant %s diverged from the device rollout - refusing to report" % name)
@@ -431,11 +449,11 @@ def run_ours(args, wl, rank, world, local_rank):
 
     # ---------------- gather the counters of every rank (the only collectives of the job; none is timed)
     vals = [float(boards) * K * R, secs, float(boards) * E, legs["f32"]["secs"]]
-    for name in ("u8", "packed", "packed_expanded", "obs_kept_on_device"):
+    for name in ("u8", "packed", "packed_expanded", "obs_kept_on_device", "device_policy"):
         vals.append(legs[name]["secs"] if name in legs else 0.0)
     if extra_local:
         owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
-        vals += [float(owl["boards"]) * 32 * oR, osecs, extra_local["children"][0]]
+        vals += [float(owl["boards"]) * 32 * oR, osecs, extra_local["children"][0]]      # columns 9, 10, 11
     allr = gather(vals)
     if rank == 0:
         total_plies, t_max = float(allr[:, 0].sum()), float(allr[:, 1].max())
@@ -467,8 +485,11 @@ def run_ours(args, wl, rank, world, local_rank):
                     leg_record("packed_expanded", 6, "returns='packed' + HostStepper.expand(): gg_host_unpack to f32 on "
                                                      "the host cores inside the timed region"),
                     host_threads=usable_cores()),
-                "obs_kept_on_device": leg_record("obs_kept_on_device", 7, "host_stepper(returns='none'): reward + done "
-                                                                          "only, observation consumed on the device"),
+                "obs_kept_on_device": leg_record("obs_kept_on_device", 7, "host_stepper(returns='none'): host actions in, "
+                                                 "reward + done out, waited for every step; observation stays on the device"),
+                "device_policy": leg_record("device_policy", 8, "BatchedGoEnv.step(actions on the device, auto_reset=True) "
+                                            "driven from Python: one gg_step launch per ply, no host copies, one "
+                                            "synchronisation at the end"),
             }
         line = {
             "metric": "env-steps/sec (batched random-legal rollout)", "value": value, "unit": "env-steps/s",
@@ -501,8 +522,8 @@ def run_ours(args, wl, rank, world, local_rank):
         }
         if extra_local:
             owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
-            o_plies, o_t = float(allr[:, 8].sum()), float(allr[:, 9].max())
-            c_t = float(allr[:, 10].max())
+            o_plies, o_t = float(allr[:, 9].sum()), float(allr[:, 10].max())
+            c_t = float(allr[:, 11].max())
             csecs, cbytes, creps = extra_local["children"]
             line["extra"] = {
                 "rollout_" + ("19x19" if owl["size"] == 19 else "9x9"): {
@@ -511,7 +532,7 @@ def run_ours(args, wl, rank, world, local_rank):
                         if world > 1 else ""),
                     "value": o_plies / o_t, "unit": "env-steps/s", "ms_per_step": 1e3 * o_t / (32 * oR),
                     "steps": 32 * oR, "preroll_plies": PREROLL, "obs": "f32",
-                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", 32, float(allr[0, 9]), oR, olaunches,
+                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", 32, float(allr[0, 10]), oR, olaunches,
                                                 peak, peak_src)},
                 "children_9x9": {
                     "workload": "gogame.children(padded=True) of 4,096 9x9 parents%s after 40 random-legal plies (seed 0): "

@@ -45,6 +45,48 @@ def test_full_batch_rollout_equals_host_simulation(n, boards, plies, ppl):
     assert not status.any() and np.array_equal(want, last[idx])
 
 
+@pytest.mark.parametrize("n,boards,kernel_name", ((9, 65536, "k_rollout_tpb"), (19, 16384, "k_rollout (")))
+def test_deep_rollout_soak_against_c_oracle(n, boards, kernel_name):
+    """The HEADLINE kernels at the headline batch sizes and launch shape (32 plies per launch into a 32-slot float32
+    ring, like bench.py): 320 plies from empty boards (9x9 games last ~124 plies, so boards finish, restart and
+    de-synchronise; 19x19 boards fill up to the mid-game), with a strided 1/64 sample of the boards replayed through
+    the C oracle at EVERY ply - next state bit for bit, legality of the sampled action, done flag, REAL reward."""
+    from gymgo_b200.engine import GoEngine
+    e = GoEngine(n, "cuda:0")
+    assert e.lib.gg_rollout_kernel(n, boards).decode().startswith(kernel_name)
+    ppl, launches, seed, board0 = 32, 10, 2024, 123_456_789
+    idx = torch.arange(0, boards, 64, device="cuda")
+    rec = e.new_records(boards)
+    ring = e.empty((ppl, boards, 6, n, n), dtype=torch.float32)
+    acts = torch.empty((ppl, boards), dtype=torch.int32, device="cuda")
+    dones = torch.empty((ppl, boards), dtype=torch.uint8, device="cuda")
+    rews = torch.empty((ppl, boards), dtype=torch.float32, device="cuda")
+    prev = np.zeros((len(idx), 6, n, n), dtype=np.uint8)
+    checked = ended = 0
+    for launch in range(launches):
+        e.rollout(rec, seed, board0, launch * ppl, ppl, plies_per_launch=ppl, actions_log=acts, obs_ring=ring,
+                  done_log=dones, reward_log=rews, reward_mode=1, komi=0.5)
+        obs = ring[:, idx].to(torch.uint8).cpu().numpy()               # ply p of this launch sits in slot p (32 | t0)
+        a, d, r = acts[:, idx].cpu().numpy(), dones[:, idx].cpu().numpy(), rews[:, idx].cpu().numpy()
+        for p in range(ppl):
+            prev[prev[:, 5, 0, 0] == 1] = 0                             # auto-reset precedes the ply
+            want, status = co.batch_next_states(prev, a[p])
+            assert not status.any(), (launch, p, "sampled an illegal action")
+            assert np.array_equal(want, obs[p]), (launch, p)
+            over = want[:, 5, 0, 0] == 1
+            assert np.array_equal(d[p], over.astype(np.uint8))
+            ar = co.batch_areas(want).astype(np.float64)
+            want_r = np.where(over, np.sign(ar[:, 0] - ar[:, 1] - 0.5), 0.0)
+            assert np.array_equal(r[p].astype(np.float64), want_r)
+            prev = want
+            checked += len(idx)
+            ended += int(over.sum())
+    assert checked == launches * ppl * len(idx) and (ended > 0 or n == 19)
+    # the records the kernel left behind are the sampled boards' last states
+    assert np.array_equal(e.unpack(rec[idx], dtype=torch.uint8).cpu().numpy(), prev)
+    invariants(e.unpack(rec, dtype=torch.uint8).cpu().numpy())
+
+
 def test_children_full_config():
     """configs[3]: 9x9 children() of 4,096 parents after 40 random plies; every slot against per-action gg_step,
     a sample against the C oracle."""
