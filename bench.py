@@ -14,8 +14,9 @@ What is timed, whatever K/W the caller passes (SURVEY.md 8d defines the metric a
   2. W warm-up steps with all outputs;
   3. the timed region: R repetitions of exactly K steps, R chosen (from an untimed trial, same R on every rank)
      so that the region lasts >= MIN_TIMED_MS of device time; `ms_per_step` is the mean over R*K steps.
-The persistent kernel plays min(K, plies_per_launch) plies per launch into an observation ring with one slot per
-ply of a launch: every observation of a launch stays readable until the next launch (ring bytes >> L2).
+The R*K plies are played by the persistent kernel in launches of plies_per_launch (128) plies - launch boundaries do
+not follow K - into an observation ring with one slot per ply of a launch: every observation of a launch stays
+readable until the next launch (ring bytes >> L2).  Launches are dynamically scheduled (gg_rollout_with + workspace).
 
 The JSON line also carries `extra`: the other BASELINE configs measured in the same run - 19x19 x 16,384
 (configs[2]; per GPU this is configs[4] at --gpus 8) and children() of 4,096 9x9 parents (configs[3]) - and `e2e`:
@@ -252,12 +253,11 @@ class RolloutBench(object):
         return launches
 
     def timed(self, k, repeats):
+        """the timed region: repeats * k consecutive plies (launch boundaries every `ppl` plies, not every k)"""
         import torch
         ev0, ev1 = _events()
         ev0.record()
-        launches = 0
-        for _ in range(repeats):
-            launches += self.plies(k)
+        launches = self.plies(k * repeats)
         ev1.record()
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / 1e3, launches
@@ -277,7 +277,8 @@ def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches,
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": profiled_traffic(size, obs_name, plies_in_launch),
             "algorithmic_bytes_per_launch": per_launch, "plies_per_launch": plies_in_launch,
-            "kernel": "gg::%s, Geo<%d>" % (eng.lib.gg_rollout_kernel(size, boards).decode(), size),
+            "kernel": "gg::%s, Geo<%d>, dynamically scheduled in 4-ply blocks" % (
+                eng.lib.gg_rollout_kernel(size, boards).decode(), size),
             "bytes_per_ply": bytes_per_ply, "peak_source": peak_src, "launch_us": launch_s * 1e6,
             "timing": "CUDA events on the launching stream around %d launches" % launches}
 
@@ -320,7 +321,7 @@ def run_ours(args, wl, rank, world, local_rank):
     eng = GoEngine(size, dev)
     board0 = rank * boards
     K, W = args.steps, args.warmup
-    ppl = max(1, min(args.plies_per_launch, K))
+    ppl = max(1, args.plies_per_launch)
     peak, peak_src = measured_peak_gbs()
 
     def barrier():
@@ -434,12 +435,12 @@ def run_ours(args, wl, rank, world, local_rank):
         other = "19x19" if args.workload == "9x9" else "9x9"
         owl = WORKLOADS[other]
         oeng = GoEngine(owl["size"], dev)
-        ob = RolloutBench(oeng, owl["boards"], rank * owl["boards"], torch.float32, 4, 32)
-        ob.plies(32)
-        ot, _ = ob.timed(32, 1)
+        ob = RolloutBench(oeng, owl["boards"], rank * owl["boards"], torch.float32, 4, ppl)
+        ob.plies(ppl)
+        ot, _ = ob.timed(ppl, 1)
         oR = pick_repeats(float(gather([ot])[:, 0].max()))
         barrier()
-        osecs, olaunches = ob.timed(32, oR)
+        osecs, olaunches = ob.timed(ppl, oR)
         barrier()
         extra_local["rollout"] = (owl, oeng, osecs, oR, olaunches)
         del ob
@@ -453,7 +454,7 @@ def run_ours(args, wl, rank, world, local_rank):
         vals.append(legs[name]["secs"] if name in legs else 0.0)
     if extra_local:
         owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
-        vals += [float(owl["boards"]) * 32 * oR, osecs, extra_local["children"][0]]      # columns 9, 10, 11
+        vals += [float(owl["boards"]) * ppl * oR, osecs, extra_local["children"][0]]      # columns 9, 10, 11
     allr = gather(vals)
     if rank == 0:
         total_plies, t_max = float(allr[:, 0].sum()), float(allr[:, 1].max())
@@ -530,9 +531,9 @@ def run_ours(args, wl, rank, world, local_rank):
                     "workload": owl["name"] + (" per GPU; x%d GPUs = %d boards%s" % (
                         world, owl["boards"] * world, " = configs[4]" if owl["size"] == 19 and world == 8 else "")
                         if world > 1 else ""),
-                    "value": o_plies / o_t, "unit": "env-steps/s", "ms_per_step": 1e3 * o_t / (32 * oR),
-                    "steps": 32 * oR, "preroll_plies": PREROLL, "obs": "f32",
-                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", 32, float(allr[0, 10]), oR, olaunches,
+                    "value": o_plies / o_t, "unit": "env-steps/s", "ms_per_step": 1e3 * o_t / (ppl * oR),
+                    "steps": ppl * oR, "preroll_plies": PREROLL, "obs": "f32",
+                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", ppl, float(allr[0, 10]), oR, olaunches,
                                                 peak, peak_src)},
                 "children_9x9": {
                     "workload": "gogame.children(padded=True) of 4,096 9x9 parents%s after 40 random-legal plies (seed 0): "
@@ -573,8 +574,9 @@ def main():
     ap.add_argument("--boards", type=int, default=None, help="boards per GPU (default: the workload's)")
     ap.add_argument("--obs", default="f32", choices=["f32", "u8", "bf16"])
     ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--plies-per-launch", type=int, default=32,
-                    help="plies the persistent rollout kernel plays per launch (boards stay in registers)")
+    ap.add_argument("--plies-per-launch", type=int, default=128,
+                    help="plies the persistent rollout kernel plays per launch = slots of the observation ring (128 = one "
+                         "PPO-style rollout segment per launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline + f32 e2e only (no extra configs, no e2e variants)")
     args = ap.parse_args()

@@ -20,7 +20,7 @@ GG_VERSION = 200
 GG_REWARD_NONE, GG_REWARD_REAL, GG_REWARD_HEURISTIC = 0, 1, 2
 
 EXPORTS = ("gg_version", "gg_last_cuda_error", "gg_supported", "gg_set_device", "gg_layout", "gg_pack", "gg_unpack", "gg_reset",
-           "gg_step", "gg_rollout_step", "gg_rollout", "gg_rollout_with", "gg_rollout_kernel", "gg_kernel_name", "gg_update_pieces", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
+           "gg_step", "gg_rollout_step", "gg_rollout", "gg_rollout_with", "gg_rollout_workspace_bytes", "gg_rollout_kernel", "gg_kernel_name", "gg_update_pieces", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
            "gg_canonical", "gg_symmetry", "gg_host_unpack")
 
 _ERR = {GG_EINVAL: "GG_EINVAL (bad argument)", GG_ESIZE: "GG_ESIZE (board size not supported, build has 2..19)",
@@ -71,7 +71,9 @@ def lib():
     L.gg_step.argtypes = [vp, vp, vp, vp, i64, i32, u32, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout_step.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, i32, f32, vp]
     L.gg_rollout.argtypes = [vp, i64, i32, u64, u64, u64, i32, i32, vp, vp, i32, i32, vp, vp, i32, f32, vp]
-    L.gg_rollout_with.argtypes = [i32] + L.gg_rollout.argtypes
+    L.gg_rollout_with.argtypes = [i32] + L.gg_rollout.argtypes[:-1] + [vp, i64, i32, vp]
+    L.gg_rollout_workspace_bytes.argtypes = [i32, i64]
+    L.gg_rollout_workspace_bytes.restype = i64
     L.gg_rollout_kernel.argtypes = [i32, i64]
     L.gg_rollout_kernel.restype = ctypes.c_char_p
     L.gg_kernel_name.argtypes = [i32]

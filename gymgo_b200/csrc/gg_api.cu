@@ -197,9 +197,19 @@ GG_API int gg_rollout_step(void* rec, int64_t batch, int n, uint64_t seed, uint6
     return finish(v->step(a, MODE_ROLLOUT, static_cast<cudaStream_t>(stream)));
 }
 
+// workspace of the dynamically scheduled rollout: one ticket counter + one progress word per tile (tiles hold >= 8 boards)
+static int64_t rollout_workspace_bytes(int64_t batch) { return ((batch / 8 + 2) * 4 + 15) / 16 * 16; }
+// plies per scheduling block when the caller passes 0: measured best 3..5 on both headline configs
+// (tools/sweep_block_plies.py, profiles/r02_block_plies_sweep.json)
+static const int kDefaultBlockPlies = 4;
+
+GG_API int64_t gg_rollout_workspace_bytes(int n, int64_t batch) {
+    return (lookup(n) && batch >= 0) ? rollout_workspace_bytes(batch) : GG_ESIZE;
+}
 GG_API int gg_rollout_with(int kernel, void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0, int steps,
                     int plies_per_launch, int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring,
-                    uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* stream) {
+                    uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* workspace,
+                    int64_t workspace_bytes, int block_plies, void* stream) {
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
     if (batch < 0 || steps < 0 || plies_per_launch < 1 || (batch > 0 && !rec)) return GG_EINVAL;
@@ -219,9 +229,18 @@ GG_API int gg_rollout_with(int kernel, void* rec, int64_t batch, int n, uint64_t
     a.obs_dtype = obs_dtype;
     a.ring = obs_ring_buf ? obs_ring : 1;
     a.variant = kernel == GG_KERNEL_AUTO ? auto_kernel(v, batch) : kernel;
+    if (workspace && (workspace_bytes < rollout_workspace_bytes(batch) || !aligned16(workspace))) return GG_EINVAL;
+    if (block_plies < 0) return GG_EINVAL;
+    a.block_plies = block_plies > 0 ? block_plies : kDefaultBlockPlies;
     for (int p = 0; p < steps; p += plies_per_launch) {
         a.t0 = t0 + uint64_t(p);
         a.plies = steps - p < plies_per_launch ? steps - p : plies_per_launch;
+        a.ws = nullptr;
+        if (workspace && a.plies >= 2 * a.block_plies) {           // long launches are scheduled dynamically
+            cudaError_t e = cudaMemsetAsync(workspace, 0, size_t(rollout_workspace_bytes(batch)), static_cast<cudaStream_t>(stream));
+            if (e != cudaSuccess) return finish(e);
+            a.ws = static_cast<int*>(workspace);
+        }
         a.actions_log = actions_log ? actions_log + size_t(p) * size_t(batch) : nullptr;
         a.done_log = done_log ? done_log + size_t(p) * size_t(batch) : nullptr;
         a.reward_log = (reward_log && reward_mode != GG_REWARD_NONE) ? reward_log + size_t(p) * size_t(batch) : nullptr;
@@ -235,7 +254,7 @@ GG_API int gg_rollout(void* rec, int64_t batch, int n, uint64_t seed, uint64_t b
                int plies_per_launch, int32_t* actions_log, void* obs_ring_buf, int obs_dtype, int obs_ring,
                uint8_t* done_log, float* reward_log, int reward_mode, float komi, void* stream) {
     return gg_rollout_with(GG_KERNEL_AUTO, rec, batch, n, seed, board0, t0, steps, plies_per_launch, actions_log, obs_ring_buf,
-                           obs_dtype, obs_ring, done_log, reward_log, reward_mode, komi, stream);
+                           obs_dtype, obs_ring, done_log, reward_log, reward_mode, komi, nullptr, 0, 0, stream);
 }
 
 GG_API const char* gg_rollout_kernel(int n, int64_t batch) {

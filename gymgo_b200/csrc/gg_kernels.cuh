@@ -65,6 +65,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// gpu-scope acquire / release on a global flag, and the generic <-> async proxy fence that orders them against TMA
+// traffic to global memory (records written by one CTA's bulk store are read by another CTA's bulk load)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -553,7 +564,49 @@ struct RolloutArgs {
     void* obs_ring;             // [ring, B, 6, N, N] or NULL; ply t writes slot t % ring
     int obs_dtype, ring;
     int variant;                // 0: k_rollout (lane-sliced boards), 1: k_rollout_tpb (thread per board)
+    // Dynamic scheduling (ws != NULL): the launch is cut into `rounds` blocks of `block_plies` plies; the grid has
+    // tiles * rounds CTAs, each takes a ticket (atomicAdd on ws[0]) = (round, tile) in round-major order, waits until
+    // the tile's previous block is finished (ws[1 + tile] >= round), plays its block and publishes ws[1 + tile] =
+    // round + 1.  Tickets are handed out in start order, so the CTA a ticket waits for is always running or done.
+    // The hardware block scheduler thereby balances the (persistently unequal) per-tile work over the SMs.
+    int* ws;
+    int block_plies, rounds;
+    long long tiles;
 };
+
+// (round, tile, ply range) of this CTA; static scheduling: the whole launch for tile blockIdx.x
+struct WorkItem {
+    long long tile;
+    int round, p_lo, p_hi;
+};
+__device__ __forceinline__ WorkItem take_work(const RolloutArgs& a, int* s_ticket, int tid) {
+    WorkItem w;
+    w.tile = blockIdx.x;
+    w.round = 0;
+    w.p_lo = 0;
+    w.p_hi = a.plies;
+    if (a.ws) {
+        if (tid == 0) *s_ticket = atomicAdd(a.ws, 1);
+        __syncthreads();
+        const long long ticket = *s_ticket;
+        w.round = int(ticket / a.tiles);
+        w.tile = ticket - (long long)w.round * a.tiles;
+        w.p_lo = w.round * a.block_plies;
+        w.p_hi = w.p_lo + a.block_plies < a.plies ? w.p_lo + a.block_plies : a.plies;
+        if (w.round > 0 && tid == 0) {
+            while (ld_acquire_gpu(a.ws + 1 + w.tile) < w.round) __nanosleep(200);
+            fence_proxy_async_all();                               // the records arrive through the async proxy (TMA)
+        }
+    }
+    return w;
+}
+__device__ __forceinline__ void publish_work(const RolloutArgs& a, const WorkItem& w) {   // one thread, after its bulk
+    if (a.ws) {                                                                           // store has completed
+        fence_proxy_async_all();
+        __threadfence();
+        st_release_gpu(a.ws + 1 + w.tile, w.round + 1);
+    }
+}
 
 template <class G>
 struct WarpStream {
@@ -571,9 +624,11 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     __shared__ uint32_t s_bits_all[T::WPC][WS::W32];
     __shared__ __align__(16) float4 s_lut[LUT_F4];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile_base = (long long)blockIdx.x * T::BT;
+    const WorkItem work = take_work(a, &s_ticket, tid);
+    const long long tile_base = work.tile * T::BT;
     const long long left = a.boards - tile_base;
     const int nb = left < T::BT ? int(left) : T::BT;
     const bool want_obs = a.obs_ring != nullptr;
@@ -583,7 +638,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
         fence_mbar_init();
     }
     obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
-    __syncthreads();
+    __syncthreads();                                               // also: thread 0 has seen the tile's previous block
     if (tid == 0) {
         mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
         bulk_g2s(s_rec, a.rec + tile_base * G::REC_W32, uint32_t(nb) * G::REC_BYTES, &s_bar);
@@ -619,7 +674,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     const long long slot_elems = a.boards * WS::DENSE;
     const unsigned long long gb = a.board0 + (unsigned long long)slot;
 
-    for (int p = 0; p < a.plies; ++p) {
+    for (int p = work.p_lo; p < work.p_hi; ++p) {
         const unsigned long long t = a.t0 + (unsigned long long)p;
         if (flags & FLAG_DONE) {                                   // auto-reset (gogame.init_state)
             black = white = invd = 0;
@@ -675,6 +730,7 @@ __global__ void __launch_bounds__(Tile<G>::THREADS, Tile<G>::ROLLOUT_MIN_BLOCKS)
     if (tid == 0) {
         bulk_s2g(a.rec + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
         bulk_commit_wait_all();
+        publish_work(a, work);
     }
 }
 
@@ -704,9 +760,11 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
     __shared__ uint32_t s_bits_all[T::THREADS / 32][T::WSTREAM_W32];
     __shared__ __align__(16) float4 s_lut[LUT_F4];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile_base = (long long)blockIdx.x * T::BT;
+    const WorkItem work = take_work(a, &s_ticket, tid);
+    const long long tile_base = work.tile * T::BT;
     const long long left = a.boards - tile_base;
     const int nb = left < T::BT ? int(left) : T::BT;
     const bool want_obs = a.obs_ring != nullptr;
@@ -749,7 +807,7 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
     const long long slot_elems = a.boards * T::DENSE;
     const unsigned long long gb = a.board0 + (unsigned long long)slot;
 
-    for (int p = 0; p < a.plies; ++p) {
+    for (int p = work.p_lo; p < work.p_hi; ++p) {
         const unsigned long long t = a.t0 + (unsigned long long)p;
         if (flags & FLAG_DONE) {
             black = white = invd = o.zero();
@@ -810,15 +868,26 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
     if (tid == 0) {
         bulk_s2g(a.rec + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
         bulk_commit_wait_all();
+        publish_work(a, work);
     }
 }
 
 inline unsigned blocks_for(long long items, int per_block) { return unsigned((items + per_block - 1) / per_block); }
 
+// fills in the dynamic-scheduling fields for tiles of `tile_boards` boards; -> CTAs to launch
+inline unsigned schedule(RolloutArgs& a, int tile_boards) {
+    a.tiles = (a.boards + tile_boards - 1) / tile_boards;
+    a.rounds = 1;
+    if (a.ws && a.block_plies > 0 && a.plies >= 2 * a.block_plies) a.rounds = (a.plies + a.block_plies - 1) / a.block_plies;
+    else a.ws = nullptr;
+    return unsigned(a.tiles * a.rounds);
+}
+
 template <class G>
 struct LaunchTpb {
-    static void go(const RolloutArgs& a, cudaStream_t s) {
-        k_rollout_tpb<G><<<blocks_for(a.boards, TpbTile<G>::BT), TpbTile<G>::THREADS, 0, s>>>(a);
+    static void go(RolloutArgs a, cudaStream_t s) {
+        const unsigned grid = schedule(a, TpbTile<G>::BT);
+        k_rollout_tpb<G><<<grid, TpbTile<G>::THREADS, 0, s>>>(a);
     }
 };
 
@@ -1081,8 +1150,13 @@ struct Launch {
     }
     static cudaError_t rollout(const RolloutArgs& a, cudaStream_t s) {
         if (a.boards <= 0 || a.plies <= 0) return cudaSuccess;
-        if (a.variant == 1) LaunchTpb<G>::go(a, s);
-        else k_rollout<G><<<blocks_for(a.boards, Tile<G>::BT), Tile<G>::THREADS, 0, s>>>(a);
+        if (a.variant == 1) {
+            LaunchTpb<G>::go(a, s);
+        } else {
+            RolloutArgs b = a;
+            const unsigned grid = schedule(b, Tile<G>::BT);
+            k_rollout<G><<<grid, Tile<G>::THREADS, 0, s>>>(b);
+        }
         return cudaGetLastError();
     }
     static cudaError_t capture(uint32_t* rec, const uint32_t* touch, const int32_t* player, uint32_t* killed, long long batch,

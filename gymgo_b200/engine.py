@@ -43,6 +43,7 @@ class GoEngine(object):
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.layout = _cabi.layout(self.size)
         self.rec_bytes = self.layout["rec_bytes"]
+        self._ws = {}
 
     # ------------------------------------------------------------------ plumbing
     def _enter(self):
@@ -173,12 +174,14 @@ class GoEngine(object):
                                              _ptr(done), _ptr(areas), _ptr(reward), int(reward_mode), float(komi), s))
 
     def rollout(self, rec, seed, board0, t0, steps, plies_per_launch=32, actions_log=None, obs_ring=None,
-                done_log=None, reward_log=None, reward_mode=0, komi=0.0, kernel=_cabi.GG_KERNEL_AUTO):
+                done_log=None, reward_log=None, reward_mode=0, komi=0.0, kernel=_cabi.GG_KERNEL_AUTO, dynamic=True, block_plies=0):
         """`steps` fused rollout plies by the persistent kernel (gg_rollout), `plies_per_launch` plies per launch.
         obs_ring: [R,B,6,N,N] ring of observation slots (ply t writes slot t % R); actions_log int32 [steps,B],
         done_log uint8 [steps,B], reward_log float32 [steps,B] - all optional, preallocated (logs may be longer
         than `steps`: only the first `steps` rows are written).  kernel: GG_KERNEL_* (AUTO = the measured choice; the
-        kernels are bit-identical, the explicit values exist for A/B measurements and parity tests)."""
+        kernels are bit-identical, the explicit values exist for A/B measurements and parity tests).  dynamic: give the
+        library a scheduling workspace so that long launches are load-balanced over the SMs (same results);
+        block_plies: plies per scheduling block (0 = the library's measured default)."""
         self._check_rec(rec)
         b, steps = rec.shape[0], int(steps)
         for t, name, dt in ((actions_log, "actions_log", torch.int32), (done_log, "done_log", torch.uint8),
@@ -190,10 +193,20 @@ class GoEngine(object):
             self._check_out(obs_ring, "obs_ring", (obs_ring.shape[0], b, 6, self.size, self.size), _OBS_DTYPES)
         s = self._enter()
         ring = 0 if obs_ring is None else int(obs_ring.shape[0])
+        ws = self._workspace(b) if dynamic else None
         _cabi.check(self.lib.gg_rollout_with(int(kernel), _ptr(rec), rec.shape[0], self.size, int(seed), int(board0),
                                              int(t0), int(steps), int(plies_per_launch), _ptr(actions_log), _ptr(obs_ring),
                                              _TORCH2GG[obs_ring.dtype] if obs_ring is not None else 0, ring,
-                                             _ptr(done_log), _ptr(reward_log), int(reward_mode), float(komi), s))
+                                             _ptr(done_log), _ptr(reward_log), int(reward_mode), float(komi),
+                                             _ptr(ws), 0 if ws is None else ws.numel(), int(block_plies), s))
+
+    def _workspace(self, batch):
+        """scheduling workspace of gg_rollout_with for `batch` boards (cached; stream-ordered reuse is safe: the library
+        clears it with a memset enqueued before each launch)"""
+        ws = self._ws.get(batch)
+        if ws is None:
+            ws = self._ws[batch] = self.empty((int(self.lib.gg_rollout_workspace_bytes(self.size, batch)),))
+        return ws
 
     def sample_legal(self, rec, seed, board0, t):
         self._check_rec(rec)

@@ -145,11 +145,22 @@ GG_API int gg_rollout(void *rec, int64_t batch, int n, uint64_t seed, uint64_t b
                       int plies_per_launch, int32_t *actions_log, void *obs_ring_buf, int obs_dtype, int obs_ring,
                       uint8_t *done_log, float *reward_log, int reward_mode, float komi, void *stream);
 
-/* gg_rollout with an explicit kernel choice (GG_KERNEL_*): for A/B measurements and the kernel-vs-kernel parity
- * tests.  gg_rollout(...) == gg_rollout_with(GG_KERNEL_AUTO, ...). */
+/* gg_rollout with an explicit kernel choice (GG_KERNEL_*) and an optional scheduling workspace.
+ *   workspace    NULL, or a device buffer of >= gg_rollout_workspace_bytes(n, batch) bytes (16-byte aligned, contents
+ *                irrelevant: it is cleared by a memset enqueued before every launch).  With a workspace, launches of
+ *                >= 2 * block_plies plies are DYNAMICALLY SCHEDULED: the launch is cut into blocks of block_plies
+ *                plies and (tile, block) work items are handed to CTAs in start order (a ticket counter), each waiting
+ *                for its tile's previous block.  Boards differ persistently in cost (game phase), and a static
+ *                one-CTA-per-tile launch leaves the SMs idle ~17 % of the time at the tail
+ *                (profiles/r02_k_rollout_*_ncu_full.txt): +15 % (9x9) / +21 % (19x19) throughput.
+ *   block_plies  plies per work item; 0 = the measured default (4).
+ * Results are identical with and without a workspace.
+ * gg_rollout(...) == gg_rollout_with(GG_KERNEL_AUTO, ..., NULL, 0, 0, stream). */
 GG_API int gg_rollout_with(int kernel, void *rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t0,
                            int steps, int plies_per_launch, int32_t *actions_log, void *obs_ring_buf, int obs_dtype,
-                           int obs_ring, uint8_t *done_log, float *reward_log, int reward_mode, float komi, void *stream);
+                           int obs_ring, uint8_t *done_log, float *reward_log, int reward_mode, float komi,
+                           void *workspace, int64_t workspace_bytes, int block_plies, void *stream);
+GG_API int64_t gg_rollout_workspace_bytes(int n, int64_t batch);
 
 /* Name of the kernel GG_KERNEL_AUTO resolves to for (n, batch), and the name of kernel `kernel`. */
 GG_API const char *gg_rollout_kernel(int n, int64_t batch);

@@ -53,8 +53,12 @@ def test_rollout_kernel_choice_and_new_argument_checks():
     assert "tpb" not in lib.gg_rollout_kernel(19, 16384).decode()                      # configs[2]
     buf = ctypes.create_string_buffer(64)
     addr = ctypes.addressof(buf)
-    bad_kernel = lib.gg_rollout_with(5, addr, 4, 9, 0, 0, 0, 3, 1, None, None, 0, 0, None, None, 0, 0.0, None)
+    bad_kernel = lib.gg_rollout_with(5, addr, 4, 9, 0, 0, 0, 3, 1, None, None, 0, 0, None, None, 0, 0.0, None, 0, 0, None)
     assert bad_kernel == _cabi.GG_EINVAL
+    assert lib.gg_rollout_workspace_bytes(9, 65536) >= 4 * (65536 // 40 + 2) and lib.gg_rollout_workspace_bytes(9, 65536) % 16 == 0
+    small_ws = lib.gg_rollout_with(0, addr, 4096, 9, 0, 0, 0, 32, 32, None, None, 0, 0, None, None, 0, 0.0, addr, 16, 0, None)
+    assert small_ws == _cabi.GG_EINVAL                                   # workspace too small for the batch
+    assert lib.gg_rollout_with(0, addr, 4, 9, 0, 0, 0, 3, 1, None, None, 0, 0, None, None, 0, 0.0, None, 0, -1, None) == _cabi.GG_EINVAL
     assert lib.gg_step(addr, addr, addr, None, 4, 9, 16, None, 0, None, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
     assert lib.gg_update_pieces(addr, addr, addr, addr, 4, 9, None) == _cabi.GG_EINVAL       # killed aliases rec
     assert lib.gg_update_pieces(None, addr, addr, addr, 4, 9, None) == _cabi.GG_EINVAL

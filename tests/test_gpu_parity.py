@@ -182,21 +182,22 @@ def test_persistent_rollout_equals_single_plies(eng, n, boards, dtype):
 @pytest.mark.parametrize("n,boards", ((9, 1003), (7, 333), (5, 77), (3, 130), (8, 64), (19, 141), (13, 97), (16, 33), (2, 50)))
 @pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.float16))
 def test_rollout_kernels_are_bit_identical(eng, n, boards, dtype):
-    """the two persistent rollout kernels - lane-sliced and thread-per-board - produce the same records, observations
-    and logs (gg_rollout_with forces each)"""
+    """the two persistent rollout kernels - lane-sliced and thread-per-board - with static (one CTA per tile) and
+    dynamic ((tile, 8-ply block) work items with tickets) scheduling produce the same records, observations and logs"""
     from gymgo_b200 import _cabi
     e = eng(n)
     outs = []
-    for kernel in (_cabi.GG_KERNEL_LANES, _cabi.GG_KERNEL_THREAD):
+    for kernel, dynamic in ((_cabi.GG_KERNEL_LANES, False), (_cabi.GG_KERNEL_THREAD, False),
+                            (_cabi.GG_KERNEL_LANES, True), (_cabi.GG_KERNEL_THREAD, True)):
         rec = e.new_records(boards)
         ring = e.empty((23, boards, 6, n, n), dtype=dtype)
         ring.fill_(3)
         acts = torch.empty((22, boards), dtype=torch.int32, device="cuda")
         dones = torch.empty((22, boards), dtype=torch.uint8, device="cuda")
         rews = torch.empty((22, boards), dtype=torch.float32, device="cuda")
-        e.rollout(rec, 5, 77, 0, 150, plies_per_launch=50, kernel=kernel)
-        e.rollout(rec, 5, 77, 150, 22, plies_per_launch=6, actions_log=acts, obs_ring=ring, done_log=dones,
-                  reward_log=rews, reward_mode=2, komi=1.5, kernel=kernel)
+        e.rollout(rec, 5, 77, 0, 150, plies_per_launch=50, kernel=kernel, dynamic=dynamic)     # 7 blocks when dynamic
+        e.rollout(rec, 5, 77, 150, 22, plies_per_launch=22 if dynamic else 6, actions_log=acts, obs_ring=ring,
+                  done_log=dones, reward_log=rews, reward_mode=2, komi=1.5, kernel=kernel, dynamic=dynamic)
         torch.cuda.synchronize()
         outs.append((rec, ring, acts, dones, rews))
     for other in outs[1:]:
@@ -205,7 +206,8 @@ def test_rollout_kernels_are_bit_identical(eng, n, boards, dtype):
 
 
 @pytest.mark.parametrize("kernel", (0, 1))
-@pytest.mark.parametrize("n,boards,ppl,ring", ((19, 1000, 7, 3), (19, 64, 32, 32), (13, 500, 5, 2), (9, 2000, 9, 4), (6, 77, 3, 1)))
+@pytest.mark.parametrize("n,boards,ppl,ring", ((19, 1000, 7, 3), (19, 64, 32, 32), (13, 500, 5, 2), (9, 2000, 9, 4), (6, 77, 3, 1),
+                                               (9, 5000, 40, 3), (19, 700, 33, 2), (4, 300, 64, 5)))
 def test_rollout_small_rings_keep_the_last_ply(eng, n, boards, ppl, ring, kernel):
     """many plies per launch into rings smaller than a launch: every ring slot ends up holding the observation of the
     LAST ply mapped to it (what the single-ply kernel writes), for both persistent kernels"""

@@ -51,19 +51,20 @@ def main():
             for k in (0, 1):
                 if k == 1 and n > 9 and boards * n * n > 16384 * 361 // 2 and dname != "f32":
                     continue                                    # thread-per-board on big boards: slow, sample f32 only
-                rec = start.clone()
-                plies = 10 * args.ppl
-                e.rollout(rec, 0, 0, 256, args.ppl, plies_per_launch=args.ppl, obs_ring=ring, kernel=k)
-                torch.cuda.synchronize()
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-                e.rollout(rec, 0, 0, 256 + args.ppl, plies, plies_per_launch=args.ppl, obs_ring=ring, kernel=k)
-                ev1.record()
-                torch.cuda.synchronize()
-                us = ev0.elapsed_time(ev1) * 1e3 / plies
-                row[NAMES[k]] = round(us, 2)
-                if elem:
-                    row[NAMES[k] + "_frac"] = round(boards * bytes_per_ply(n, elem) / (us * 1e-6) / 1e9 / peak, 3)
+                for mode, dyn, bp in (("_static", False, 0), ("", True, 0)):
+                    rec = start.clone()
+                    plies = 10 * args.ppl
+                    e.rollout(rec, 0, 0, 256, args.ppl, plies_per_launch=args.ppl, obs_ring=ring, kernel=k, dynamic=dyn, block_plies=bp)
+                    torch.cuda.synchronize()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    e.rollout(rec, 0, 0, 256 + args.ppl, plies, plies_per_launch=args.ppl, obs_ring=ring, kernel=k, dynamic=dyn, block_plies=bp)
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    us = ev0.elapsed_time(ev1) * 1e3 / plies
+                    row[NAMES[k] + mode] = round(us, 2)
+                    if elem:
+                        row[NAMES[k] + mode + "_frac"] = round(boards * bytes_per_ply(n, elem) / (us * 1e-6) / 1e9 / peak, 3)
             print(json.dumps(row), flush=True)
             out["rows"].append(row)
             del ring
