@@ -267,7 +267,7 @@ def pick_repeats(trial_secs_all_ranks):
     return max(1, int(-(-MIN_TIMED_MS / 1e3 // max(trial_secs_all_ranks, 1e-6))))
 
 
-def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches, peak, peak_src):
+def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches, peak, peak_src, write_ceiling=None):
     size = eng.size
     bytes_per_ply = algorithmic_bytes_per_ply(size, obs_elem)
     plies_in_launch = repeats * k / float(launches)                   # plies one launch really played
@@ -280,7 +280,33 @@ def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches,
             "kernel": "gg::%s, Geo<%d>, dynamically scheduled in 4-ply blocks" % (
                 eng.lib.gg_rollout_kernel(size, boards).decode(), size),
             "bytes_per_ply": bytes_per_ply, "peak_source": peak_src, "launch_us": launch_s * 1e6,
+            "plain_fill_probe": None if write_ceiling is None else {
+                "gbs": write_ceiling, "achieved_over_it": achieved / write_ceiling,
+                "note": "gg_probe_write (nothing but 16-byte streaming stores, best of several run lengths) timed in this "
+                        "run.  `peak` is the driver's measured COPY bandwidth, not the hardware limit (HBM3e nominal "
+                        "~8 TB/s): frac > 1 means this kernel's store stream - every warp writing long contiguous runs - "
+                        "sustains more than that copy and more than the plain fill; ncu confirms the bytes reach DRAM "
+                        "(`traffic` ~ algorithmic bytes, dram__cycles_active 85 % / 75 % in profiles/r02_k_rollout_*)"},
             "timing": "CUDA events on the launching stream around %d launches" % launches}
+
+
+def write_ceiling_gbs(eng, buf, runs=(512, 4096, 65536, 1 << 20)):
+    """pure-write bandwidth of this GPU: gg_probe_write (16-byte streaming stores only) over `buf` (>> L2), the best over
+    a few contiguous-run lengths per warp and 4 repetitions each"""
+    import torch
+    from gymgo_b200 import _cabi
+    nbytes = min(buf.numel() * buf.element_size(), 8 << 30) // 16 * 16
+    stream = eng._enter()
+    best = 0.0
+    for run in runs:
+        for _ in range(4):
+            ev0, ev1 = _events()
+            ev0.record()
+            _cabi.check(eng.lib.gg_probe_write(buf.data_ptr(), nbytes, run, stream))
+            ev1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (ev0.elapsed_time(ev1) / 1e3) / 1e9)
+    return best
 
 
 def measure_children(eng, parents_n, board0, repeats=10):
@@ -347,6 +373,7 @@ def run_ours(args, wl, rank, world, local_rank):
     barrier()
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    write_ceiling = write_ceiling_gbs(eng, main.ring) if rank == 0 else None
 
     # ---------------- transparency: the same plies with ONE launch per ply (records reloaded and stored every ply)
     n1 = min(max(K, 20), 100)
@@ -519,7 +546,7 @@ def run_ours(args, wl, rank, world, local_rank):
                                            "and stored every ply)"},
             "clocks": clocks,
             "roofline": roofline_record(eng, boards, obs_elem, args.obs, K, float(allr[0, 1]), R, n_launches, peak,
-                                        peak_src),
+                                        peak_src, write_ceiling),
         }
         if extra_local:
             owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
@@ -534,7 +561,7 @@ def run_ours(args, wl, rank, world, local_rank):
                     "value": o_plies / o_t, "unit": "env-steps/s", "ms_per_step": 1e3 * o_t / (ppl * oR),
                     "steps": ppl * oR, "preroll_plies": PREROLL, "obs": "f32",
                     "roofline": roofline_record(oeng, owl["boards"], 4, "f32", ppl, float(allr[0, 10]), oR, olaunches,
-                                                peak, peak_src)},
+                                                peak, peak_src, write_ceiling)},
                 "children_9x9": {
                     "workload": "gogame.children(padded=True) of 4,096 9x9 parents%s after 40 random-legal plies (seed 0): "
                                 "82 child slots per parent, packed records + f32 dense states + valid mask "

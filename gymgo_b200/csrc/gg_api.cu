@@ -52,6 +52,24 @@ static bool dense_dtype_ok(int dt, bool allow_f64) {
 }
 }  // namespace gg
 
+namespace gg {
+// Measurement aid (gg_probe_write): nothing but 16-byte streaming stores, the same instruction (st.global.cs.v4) and
+// access pattern the observation emission uses - the pure-write ceiling of the GPU, which bench.py reports next to the
+// copy-based HBM peak (a copy alternates reads and writes on the DRAM bus and tops out lower than a write stream).
+static __global__ void __launch_bounds__(256) k_probe_write(float4* buf, long long vectors, long long chunk) {
+    // every warp streams contiguous runs of `chunk` vectors (like a rollout warp streams its boards' observations)
+    const float4 v = make_float4(1.f, 0.f, 1.f, 0.f);
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    for (long long base = warp * chunk; base < vectors; base += warps * chunk) {
+        const long long end = base + chunk < vectors ? base + chunk : vectors;
+#pragma unroll 4
+        for (long long i = base + lane; i < end; i += 32) __stcs(buf + i, v);
+    }
+}
+}  // namespace gg
+
 // ---------------------------------------------------------------------------------------------- host codec
 // Packed records in HOST memory -> dense [B,6,N,N] in host memory: for consumers that move the 40x smaller packed
 // records over PCIe (HostStepper(returns="packed")) and expand next to the CPU.  A codec, not a rules path: no Go
@@ -289,6 +307,14 @@ GG_API int gg_host_unpack(const void* rec_host, int64_t batch, int n, int dtype,
     else host_unpack<uint16_t>(rec, batch, n, v, dtype == GG_BF16 ? uint16_t(0x3F80) : uint16_t(0x3C00),
                                static_cast<uint16_t*>(dense_host), threads);
     return GG_OK;
+}
+
+GG_API int gg_probe_write(void* buf, int64_t bytes, int64_t run_bytes, void* stream) {
+    if (bytes < 0 || (bytes > 0 && !buf) || (bytes & 15) || run_bytes < 512 || (run_bytes & 511)) return GG_EINVAL;
+    if (!aligned16(buf)) return GG_EALIGN;
+    if (bytes == 0) return GG_OK;
+    k_probe_write<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float4*>(buf), bytes / 16, run_bytes / 16);
+    return finish(cudaGetLastError());
 }
 
 GG_API int gg_sample_legal(const void* rec, int64_t batch, int n, uint64_t seed, uint64_t board0, uint64_t t,

@@ -209,6 +209,12 @@ GG_API int gg_canonical(const void *rec_in, void *rec_out, int64_t batch, int n,
  * Replaces: random_symmetry / all_symmetries (gogame.py:340-382). */
 GG_API int gg_symmetry(const void *rec_in, void *rec_out, int64_t batch, int n, int sym, void *stream);
 
+/* Measurement aid: fill `bytes` (a multiple of 16) of device memory with 16-byte streaming stores, every warp
+ * streaming contiguous runs of `run_bytes` (a multiple of 512) - the store instruction and pattern of the observation
+ * emission and nothing else.  bench.py times it to report the pure-write ceiling of the GPU next to the copy-based
+ * HBM peak of MEASURED_PEAKS.json. */
+GG_API int gg_probe_write(void *buf, int64_t bytes, int64_t run_bytes, void *stream);
+
 /* HOST codec (the only entry point that takes host pointers and runs on the CPU): packed records in host memory ->
  * dense [B,6,N,N] of dtype in host memory, `threads` worker threads (<= 0: all hardware threads, capped at 64).
  * For consumers that fetch the packed records over PCIe instead of the 40x larger dense observation
