@@ -43,7 +43,6 @@ class GoEngine(object):
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.layout = _cabi.layout(self.size)
         self.rec_bytes = self.layout["rec_bytes"]
-        self._ws = {}
 
     # ------------------------------------------------------------------ plumbing
     def _enter(self):
@@ -201,12 +200,10 @@ class GoEngine(object):
                                              _ptr(ws), 0 if ws is None else ws.numel(), int(block_plies), s))
 
     def _workspace(self, batch):
-        """scheduling workspace of gg_rollout_with for `batch` boards (cached; stream-ordered reuse is safe: the library
-        clears it with a memset enqueued before each launch)"""
-        ws = self._ws.get(batch)
-        if ws is None:
-            ws = self._ws[batch] = self.empty((int(self.lib.gg_rollout_workspace_bytes(self.size, batch)),))
-        return ws
+        """scheduling workspace of gg_rollout_with for `batch` boards.  Allocated per call from torch's stream-aware
+        caching allocator (microseconds): two rollouts of one engine on different streams must not share tickets, and
+        a block freed while its kernel is still queued is only ever reused in stream order."""
+        return self.empty((int(self.lib.gg_rollout_workspace_bytes(self.size, batch)),))
 
     def sample_legal(self, rec, seed, board0, t):
         self._check_rec(rec)
