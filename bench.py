@@ -330,6 +330,7 @@ def measure_children(eng, parents_n, board0, repeats=10):
 
 
 def run_ours(args, wl, rank, world, local_rank):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from gymgo_b200 import hostmem, sharding
@@ -387,7 +388,7 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---------------- e2e: the public host-buffer step (BatchedGoEnv.host_stepper), copies inside the timed region.
     # The host plays the part of the policy by replaying the device rollout's own actions (recorded below), and the run
     # refuses to report if the replayed boards do not end up identical to the device rollout's.
-    E = min(max(K, 20), 300) if args.e2e_steps is None else max(1, args.e2e_steps)
+    E = min(max(K, 100), 300) if args.e2e_steps is None else max(1, args.e2e_steps)
     We = min(W, 20)
     start_rec = main.rec.clone()
     t_start = main.t
@@ -397,34 +398,35 @@ def run_ours(args, wl, rank, world, local_rank):
     replay_host = torch.empty((We + E, boards), dtype=torch.int32, pin_memory=True)
     replay_host.copy_(replay)
     torch.cuda.synchronize()
+    replay_np = replay_host.numpy()          # the host-side "policy" hands its actions over with a plain memcpy
     del main
 
-    def e2e_leg(returns, dtype, expand=False):
+    def e2e_leg(returns, dtype, transport="dense"):
         env = BatchedGoEnv(boards, size, reward_method="real", device=dev, obs_dtype=dtype, board_offset=board0)
         env.rec.copy_(start_rec)
         env.done.copy_(((eng.flags(start_rec) >> 2) & 1).to(torch.uint8))
-        hs = env.host_stepper(returns=returns, auto_reset=True, follow_current_stream=False)
-        dense = torch.empty((boards, 6, size, size), dtype=torch.float32) if expand else None
+        hs = env.host_stepper(returns=returns, auto_reset=True, follow_current_stream=False, transport=transport)
+        act_np = hs.actions.numpy()
         torch.cuda.synchronize()                                         # set-up above ran on the default stream
         for t in range(We):
-            hs.actions.copy_(replay_host[t])
+            np.copyto(act_np, replay_np[t])
             hs.step()
         barrier()
         ev0, ev1 = _events()
         wall = time.time()
         ev0.record()
         for t in range(We, We + E):
-            hs.actions.copy_(replay_host[t])                              # the "policy": host memory -> pinned buffer
-            hs.step()                                                     # H2D, one kernel, D2H, wait
-            if expand:
-                hs.expand(out=dense)                                      # packed records -> f32 on the host cores
+            np.copyto(act_np, replay_np[t])                               # the "policy": host memory -> pinned buffer
+            hs.step()                                                     # H2D, one kernel, D2H (+ host codec), wait
         ev1.record()
         torch.cuda.synchronize()
         wall = time.time() - wall
         barrier()
         ok = torch.equal(env.rec, final_rec)
+        if hs.host_expanded_bytes:                                        # the last host-expanded observation == the boards
+            ok = ok and torch.equal(hs.obs, eng.unpack(final_rec, dtype=dtype).cpu())
         return dict(secs=ev0.elapsed_time(ev1) / 1e3, wall=wall, h2d=hs.h2d_bytes, d2h=hs.d2h_bytes, ok=ok,
-                    placement=hs.placement)
+                    placement=hs.placement, host_bytes=hs.host_expanded_bytes, threads=hs.threads, transport=hs.transport)
 
     def device_policy_leg():
         """BatchedGoEnv.step driven from Python with the actions already on the device (a device-resident policy):
@@ -443,13 +445,13 @@ def run_ours(args, wl, rank, world, local_rank):
         barrier()
         return dict(secs=ev0.elapsed_time(ev1) / 1e3, h2d=0, d2h=0, ok=torch.equal(env.rec, final_rec), placement=None)
 
-    legs = {"f32": e2e_leg("obs", obs_dtype)}
+    legs = {"f32": e2e_leg("obs", obs_dtype, transport="auto")}           # the public default
     if not legs["f32"]["ok"]:
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
     if not args.quick:
-        legs["u8"] = e2e_leg("obs", torch.uint8)
+        legs["f32_dense_over_pcie"] = e2e_leg("obs", obs_dtype, transport="dense")
+        legs["u8"] = e2e_leg("obs", torch.uint8, transport="dense")
         legs["packed"] = e2e_leg("packed", obs_dtype)
-        legs["packed_expanded"] = e2e_leg("packed", obs_dtype, expand=True)
         legs["obs_kept_on_device"] = e2e_leg("none", obs_dtype)
         legs["device_policy"] = device_policy_leg()
         for name, leg in legs.items():
@@ -476,12 +478,16 @@ def run_ours(args, wl, rank, world, local_rank):
         extra_local["children"] = (csecs, cbytes, creps)
 
     # ---------------- gather the counters of every rank (the only collectives of the job; none is timed)
-    vals = [float(boards) * K * R, secs, float(boards) * E, legs["f32"]["secs"]]
-    for name in ("u8", "packed", "packed_expanded", "obs_kept_on_device", "device_policy"):
+    vals = [float(boards) * K * R, secs, float(boards) * E]
+    leg_names = ("f32", "f32_dense_over_pcie", "u8", "packed", "obs_kept_on_device", "device_policy")
+    leg_col = {}
+    for name in leg_names:
+        leg_col[name] = len(vals)
         vals.append(legs[name]["secs"] if name in legs else 0.0)
+    xcol = len(vals)                                                   # first column of the extra configs
     if extra_local:
         owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
-        vals += [float(owl["boards"]) * ppl * oR, osecs, extra_local["children"][0]]      # columns 9, 10, 11
+        vals += [float(owl["boards"]) * ppl * oR, osecs, extra_local["children"][0]]
     allr = gather(vals)
     if rank == 0:
         total_plies, t_max = float(allr[:, 0].sum()), float(allr[:, 1].max())
@@ -491,31 +497,39 @@ def run_ours(args, wl, rank, world, local_rank):
         def e2e_value(col):
             return e2e_plies / float(allr[:, col].max())
 
-        def leg_record(name, col, api):
+        def leg_record(name, api):
             leg = legs[name]
-            return {"value": e2e_value(col), "unit": "env-steps/s", "h2d_bytes_per_step": leg["h2d"] * world,
-                    "d2h_bytes_per_step": leg["d2h"] * world,
-                    "pcie_gbs_per_gpu": (leg["h2d"] + leg["d2h"]) * E / leg["secs"] / 1e9, "api": api}
+            rec = {"value": e2e_value(leg_col[name]), "unit": "env-steps/s", "h2d_bytes_per_step": leg["h2d"] * world,
+                   "d2h_bytes_per_step": leg["d2h"] * world,
+                   "pcie_gbs_per_gpu": (leg["h2d"] + leg["d2h"]) * E / leg["secs"] / 1e9, "api": api}
+            if leg.get("host_bytes"):
+                rec["host_expanded_bytes_per_step"] = leg["host_bytes"] * world
+                rec["host_codec"] = {"threads_per_rank": leg["threads"], "path": eng.lib.gg_host_unpack_path().decode(),
+                                     "dense_gbs_per_gpu_incl_transfer": leg["host_bytes"] * E / leg["secs"] / 1e9}
+            return rec
 
-        e2e = leg_record("f32", 3, "BatchedGoEnv.host_stepper(returns='obs').step(): pinned-host int32 actions in; %s "
-                                   "observation + f32 reward + u8 done out to pinned host; H2D copy, ONE kernel "
-                                   "(gg_step with in-kernel auto-reset), D2H copies as one CUDA graph, waited for every "
-                                   "step" % args.obs)
+        e2e = leg_record("f32", "BatchedGoEnv.host_stepper(returns='obs').step() [transport='auto' -> '%s']: pinned-host int32 "
+                                "actions in; %s [B,6,N,N] observation + f32 reward + u8 done out in host memory, waited for "
+                                "every step.  H2D copy, ONE kernel (gg_step with in-kernel auto-reset) and the D2H copies "
+                                "are one CUDA graph.  transport 'packed': the packed records cross PCIe and gg_host_unpack "
+                                "(AVX-512 mask moves, streaming stores, persistent worker pool) writes the dense tensor on "
+                                "the host cores inside step() - same tensor, bit for bit (checked in this run against "
+                                "gg_unpack of the final boards); transport 'dense': the kernel writes the dense tensor on "
+                                "the device and it crosses PCIe" % (legs["f32"]["transport"], args.obs))
+        e2e["transport"] = legs["f32"]["transport"]
         e2e["steps"] = E
         e2e["replay_check"] = "boards after the host-driven replay == device rollout (bit-exact)"
         e2e["host_placement"] = dict(legs["f32"]["placement"], thread_bound_to_cpus=bound_cpus)
         if not args.quick:
             e2e["variants"] = {
-                "u8_observation": leg_record("u8", 4, "same call with obs_dtype=uint8"),
-                "packed_records": leg_record("packed", 5, "host_stepper(returns='packed'): the packed records instead of "
-                                                          "the dense observation"),
-                "packed_records_expanded_on_host": dict(
-                    leg_record("packed_expanded", 6, "returns='packed' + HostStepper.expand(): gg_host_unpack to f32 on "
-                                                     "the host cores inside the timed region"),
-                    host_threads=usable_cores()),
-                "obs_kept_on_device": leg_record("obs_kept_on_device", 7, "host_stepper(returns='none'): host actions in, "
+                "f32_dense_over_pcie": leg_record("f32_dense_over_pcie", "host_stepper(returns='obs', transport='dense'): the "
+                                                  "dense f32 tensor is written on the device and crosses PCIe (round 1's e2e)"),
+                "u8_observation": leg_record("u8", "transport='dense' with obs_dtype=uint8"),
+                "packed_records": leg_record("packed", "host_stepper(returns='packed'): the packed records only, no dense "
+                                                       "tensor anywhere"),
+                "obs_kept_on_device": leg_record("obs_kept_on_device", "host_stepper(returns='none'): host actions in, "
                                                  "reward + done out, waited for every step; observation stays on the device"),
-                "device_policy": leg_record("device_policy", 8, "BatchedGoEnv.step(actions on the device, auto_reset=True) "
+                "device_policy": leg_record("device_policy", "BatchedGoEnv.step(actions on the device, auto_reset=True) "
                                             "driven from Python: one gg_step launch per ply, no host copies, one "
                                             "synchronisation at the end"),
             }
@@ -550,8 +564,8 @@ def run_ours(args, wl, rank, world, local_rank):
         }
         if extra_local:
             owl, oeng, osecs, oR, olaunches = extra_local["rollout"]
-            o_plies, o_t = float(allr[:, 9].sum()), float(allr[:, 10].max())
-            c_t = float(allr[:, 11].max())
+            o_plies, o_t = float(allr[:, xcol].sum()), float(allr[:, xcol + 1].max())
+            c_t = float(allr[:, xcol + 2].max())
             csecs, cbytes, creps = extra_local["children"]
             line["extra"] = {
                 "rollout_" + ("19x19" if owl["size"] == 19 else "9x9"): {
@@ -560,7 +574,7 @@ def run_ours(args, wl, rank, world, local_rank):
                         if world > 1 else ""),
                     "value": o_plies / o_t, "unit": "env-steps/s", "ms_per_step": 1e3 * o_t / (ppl * oR),
                     "steps": ppl * oR, "preroll_plies": PREROLL, "obs": "f32",
-                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", ppl, float(allr[0, 10]), oR, olaunches,
+                    "roofline": roofline_record(oeng, owl["boards"], 4, "f32", ppl, float(allr[0, xcol + 1]), oR, olaunches,
                                                 peak, peak_src, write_ceiling)},
                 "children_9x9": {
                     "workload": "gogame.children(padded=True) of 4,096 9x9 parents%s after 40 random-legal plies (seed 0): "

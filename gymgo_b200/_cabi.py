@@ -21,7 +21,7 @@ GG_REWARD_NONE, GG_REWARD_REAL, GG_REWARD_HEURISTIC = 0, 1, 2
 
 EXPORTS = ("gg_version", "gg_last_cuda_error", "gg_supported", "gg_set_device", "gg_layout", "gg_pack", "gg_unpack", "gg_reset",
            "gg_step", "gg_rollout_step", "gg_rollout", "gg_rollout_with", "gg_rollout_workspace_bytes", "gg_rollout_kernel", "gg_kernel_name", "gg_update_pieces", "gg_sample_legal", "gg_valid_moves", "gg_children", "gg_areas",
-           "gg_canonical", "gg_symmetry", "gg_host_unpack", "gg_probe_write")
+           "gg_canonical", "gg_symmetry", "gg_host_unpack", "gg_host_unpack_path", "gg_probe_write")
 
 _ERR = {GG_EINVAL: "GG_EINVAL (bad argument)", GG_ESIZE: "GG_ESIZE (board size not supported, build has 2..19)",
         GG_EALIGN: "GG_EALIGN (buffer not 16-byte aligned)", GG_ECUDA: "GG_ECUDA"}
@@ -86,6 +86,7 @@ def lib():
     L.gg_canonical.argtypes = [vp, vp, i64, i32, vp]
     L.gg_symmetry.argtypes = [vp, vp, i64, i32, i32, vp]
     L.gg_host_unpack.argtypes = [vp, i64, i32, i32, vp, i32]
+    L.gg_host_unpack_path.restype = ctypes.c_char_p
     L.gg_probe_write.argtypes = [vp, i64, i64, vp]
     for name in EXPORTS:
         getattr(L, name)                # fail early if a symbol is missing

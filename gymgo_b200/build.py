@@ -20,6 +20,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libgymgo_b200.so")
 SIZES = list(range(2, 20))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+HOST_FLAGS = ["-std=c++17", "-O3", "-fPIC", "-fvisibility=hidden", "-pthread"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + ARCH
 
 
@@ -39,7 +40,7 @@ def source_digest():
     for p in _sources():
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + HOST_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -69,6 +70,9 @@ def build(force=False, verbose=False):
         jobs.append((obj, [cc] + NVCC_FLAGS + ["-DGG_N=%d" % n, "-c", os.path.join(CSRC, "gg_size.cu"), "-o", obj]))
     api = os.path.join(OBJDIR, "gg_api.o")
     jobs.append((api, [cc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "gg_api.cu"), "-o", api]))
+    host = os.path.join(OBJDIR, "gg_host.o")                    # host codec: plain C++ (AVX-512 paths picked at run time)
+    jobs.append((host, [os.environ.get("CXX") or shutil.which("g++") or "g++"] + HOST_FLAGS
+                 + ["-c", os.path.join(CSRC, "gg_host.cpp"), "-o", host]))
     with concurrent.futures.ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 2)) as ex:
         for out in ex.map(lambda j: _run(j[1]), jobs):
             if verbose and out.strip():

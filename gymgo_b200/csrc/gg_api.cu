@@ -4,9 +4,9 @@
 #include <string.h>
 
 #include <thread>
-#include <vector>
 
 #include "../../include/gymgo_b200.h"
+#include "gg_host.h"
 #include "gg_kernels.cuh"
 
 namespace gg {
@@ -67,52 +67,6 @@ static __global__ void __launch_bounds__(256) k_probe_write(float4* buf, long lo
 #pragma unroll 4
         for (long long i = base + lane; i < end; i += 32) __stcs(buf + i, v);
     }
-}
-}  // namespace gg
-
-// ---------------------------------------------------------------------------------------------- host codec
-// Packed records in HOST memory -> dense [B,6,N,N] in host memory: for consumers that move the 40x smaller packed
-// records over PCIe (HostStepper(returns="packed")) and expand next to the CPU.  A codec, not a rules path: no Go
-// logic runs on the host.
-namespace gg {
-template <class T>
-static void host_unpack_range(const uint8_t* rec, int64_t b0, int64_t b1, int n, const SizeVTable* v, T one, T* dense) {
-    const int np = n * n, s = n + 1, word_bytes = v->wordbits / 8, plane_bytes = v->lpb * word_bytes;
-    for (int64_t b = b0; b < b1; ++b) {
-        const uint8_t* r = rec + b * v->rec_bytes;
-        T* out = dense + b * 6 * np;
-        uint32_t flags;
-        memcpy(&flags, r + 3 * plane_bytes, 4);
-        const int chan_of_plane[3] = {0, 1, 3};
-        for (int p = 0; p < 3; ++p) {
-            T* o = out + chan_of_plane[p] * np;
-            for (int row = 0; row < n; ++row) {
-                const int j = row / v->rpl;
-                uint64_t w = 0;
-                memcpy(&w, r + p * plane_bytes + j * word_bytes, word_bytes);
-                const uint64_t bits = w >> ((row - j * v->rpl) * s);
-                for (int c = 0; c < n; ++c) o[row * n + c] = ((bits >> c) & 1) ? one : T(0);
-            }
-        }
-        const T turn = (flags & FLAG_TURN) ? one : T(0), pass = (flags & FLAG_PASS) ? one : T(0), done = (flags & FLAG_DONE) ? one : T(0);
-        for (int i = 0; i < np; ++i) {
-            out[2 * np + i] = turn;
-            out[4 * np + i] = pass;
-            out[5 * np + i] = done;
-        }
-    }
-}
-template <class T>
-static void host_unpack(const uint8_t* rec, int64_t batch, int n, const SizeVTable* v, T one, T* dense, int threads) {
-    if (threads <= 1 || batch < 4096) return host_unpack_range<T>(rec, 0, batch, n, v, one, dense);
-    std::vector<std::thread> pool;
-    const int64_t per = (batch + threads - 1) / threads;
-    for (int t = 0; t < threads; ++t) {
-        const int64_t b0 = t * per, b1 = b0 + per < batch ? b0 + per : batch;
-        if (b0 >= b1) break;
-        pool.emplace_back([=] { host_unpack_range<T>(rec, b0, b1, n, v, one, dense); });
-    }
-    for (auto& th : pool) th.join();
 }
 }  // namespace gg
 
@@ -300,14 +254,11 @@ GG_API int gg_host_unpack(const void* rec_host, int64_t batch, int n, int dtype,
     if (batch < 0 || !dense_dtype_ok(dtype, true) || (batch > 0 && (!rec_host || !dense_host))) return GG_EINVAL;
     if (threads <= 0) threads = int(std::thread::hardware_concurrency());
     if (threads > 64) threads = 64;
-    const uint8_t* rec = static_cast<const uint8_t*>(rec_host);
-    if (dtype == GG_U8) host_unpack<uint8_t>(rec, batch, n, v, uint8_t(1), static_cast<uint8_t*>(dense_host), threads);
-    else if (dtype == GG_F32) host_unpack<float>(rec, batch, n, v, 1.0f, static_cast<float*>(dense_host), threads);
-    else if (dtype == GG_F64) host_unpack<double>(rec, batch, n, v, 1.0, static_cast<double*>(dense_host), threads);
-    else host_unpack<uint16_t>(rec, batch, n, v, dtype == GG_BF16 ? uint16_t(0x3F80) : uint16_t(0x3C00),
-                               static_cast<uint16_t*>(dense_host), threads);
+    host_unpack(static_cast<const uint8_t*>(rec_host), batch, n, v->lpb, v->rpl, v->wordbits, v->rec_bytes, dtype, dense_host,
+                threads < 1 ? 1 : threads);
     return GG_OK;
 }
+GG_API const char* gg_host_unpack_path(void) { return host_unpack_path(); }
 
 GG_API int gg_probe_write(void* buf, int64_t bytes, int64_t run_bytes, void* stream) {
     if (bytes < 0 || (bytes > 0 && !buf) || (bytes & 15) || run_bytes < 512 || (run_bytes & 511)) return GG_EINVAL;

@@ -58,23 +58,22 @@ class BatchedGoEnv(object):
         step() to avoid an extra device copy"""
         return self._step_actions
 
-    def _enqueue_step(self, auto_reset):
+    def _enqueue_step(self, auto_reset, want_obs=True):
         """enqueue one ply (finished boards restart first when auto_reset) on torch's current stream: ONE kernel launch
         (GG_STEP_AUTO_RESET does the reset inside gg_step).  Inputs/outputs are the env's static tensors, so the
         argument tuples are built once and the launch can be captured into a CUDA graph."""
         e = self.engine
         s = e._enter()
         if self._c_args is None:
-            def args(flags):
+            def args(flags, obs):
                 return (self.rec.data_ptr(), self._step_actions.data_ptr(), self.rec.data_ptr(), self.status.data_ptr(),
-                        self.batch_size, self.size, flags, self.obs.data_ptr(), _TORCH2GG[self.obs_dtype],
+                        self.batch_size, self.size, flags, self.obs.data_ptr() if obs else None, _TORCH2GG[self.obs_dtype],
                         self.done.data_ptr(), None, self.reward.data_ptr(), self.reward_mode, float(self.komi))
-            self._c_args = {False: args(_cabi.GG_STEP_REFUSE_DONE),
-                            True: args(_cabi.GG_STEP_REFUSE_DONE | _cabi.GG_STEP_AUTO_RESET),
-                            "skip": args(_cabi.GG_STEP_REFUSE_DONE | _cabi.GG_STEP_AUTO_RESET
-                                         | _cabi.GG_STEP_RESET_SKIPS_ACTION)}
+            modes = {False: _cabi.GG_STEP_REFUSE_DONE, True: _cabi.GG_STEP_REFUSE_DONE | _cabi.GG_STEP_AUTO_RESET,
+                     "skip": _cabi.GG_STEP_REFUSE_DONE | _cabi.GG_STEP_AUTO_RESET | _cabi.GG_STEP_RESET_SKIPS_ACTION}
+            self._c_args = {(k, obs): args(f, obs) for k, f in modes.items() for obs in (True, False)}
             self._gg_step = e.lib.gg_step
-        rc = self._gg_step(*self._c_args[auto_reset if auto_reset == "skip" else bool(auto_reset)], s)
+        rc = self._gg_step(*self._c_args[(auto_reset if auto_reset == "skip" else bool(auto_reset), bool(want_obs))], s)
         if rc:
             _cabi.check(rc)
 
@@ -113,10 +112,11 @@ class BatchedGoEnv(object):
                                   "status %d" % int(self.status[i])))
         return self.obs, self.reward, self.done, {"status": self.status}
 
-    def host_stepper(self, returns="obs", auto_reset=True, use_cuda_graph=True, follow_current_stream=True):
+    def host_stepper(self, returns="obs", auto_reset=True, use_cuda_graph=True, follow_current_stream=True,
+                     transport="auto", threads=0):
         """-> HostStepper: the step with HOST buffers (pinned actions in, pinned results out); see the class"""
         return HostStepper(self, returns=returns, auto_reset=auto_reset, use_cuda_graph=use_cuda_graph,
-                           follow_current_stream=follow_current_stream)
+                           follow_current_stream=follow_current_stream, transport=transport, threads=threads)
 
     def random_step(self):
         """fused: auto-reset finished boards, draw a uniformly random legal action (incl. pass), play it.
@@ -183,13 +183,34 @@ class HostStepper(object):
                       the host (gg_host_unpack, multi-threaded C++)
              "none"   reward and done only (the observation is consumed on the device)
     reward (f32 [B]) and done (u8 [B]) always come back, in one copy.
+    transport (returns="obs" only): how the observation reaches host memory -
+             "dense"  the kernel writes the dense tensor on the device and it crosses PCIe (bus-bound: 127.7 MB per
+                      9x9 x 65,536 f32 step);
+             "packed" the kernel writes NO dense tensor: the packed records cross PCIe (40x fewer bytes) and the same
+                      [B,6,N,N] tensor is expanded next to the CPU by gg_host_unpack (AVX-512 mask moves, streaming
+                      stores, `threads` workers - 0: this process's share of the usable cores) inside step().
+             "auto"   (default) "packed" when the host codec has its AVX-512 path and at least 4 worker threads, else
+                      "dense".  Measured on the B200 boxes (profiles/r02_host_codec_probe.json): 16 threads expand at
+                      180 GB/s of dense output, 4 threads at 53 GB/s, the dense tensor crosses PCIe at 55 GB/s on one
+                      GPU and 12 GB/s per GPU when eight GPUs share the host.
+             All return bit-identical tensors.  The codec's workers want the host cores to themselves: a caller whose
+             own CPU work leaves spinning OpenMP threads behind (torch's intra-op pool after a small CPU op) should
+             set OMP_WAIT_POLICY=passive or torch.set_num_threads(1).
     The step runs on the stepper's own stream; with follow_current_stream (default) it first waits for the work already
     enqueued on torch's current stream (e.g. an env.reset()), so mixing it with the device API is safe."""
 
-    def __init__(self, env, returns="obs", auto_reset=True, use_cuda_graph=True, follow_current_stream=True):
+    def __init__(self, env, returns="obs", auto_reset=True, use_cuda_graph=True, follow_current_stream=True,
+                 transport="auto", threads=0):
         if returns not in ("obs", "packed", "none"):
             raise ValueError("returns must be 'obs', 'packed' or 'none'")
+        if transport not in ("auto", "dense", "packed"):
+            raise ValueError("transport must be 'auto', 'dense' or 'packed'")
         self.env, self.returns, self.auto_reset = env, returns, bool(auto_reset)
+        self.threads = int(threads) if threads and int(threads) > 0 else hostmem.codec_threads()
+        if transport == "auto":
+            fast_codec = env.engine.lib.gg_host_unpack_path().startswith(b"avx512")
+            transport = "packed" if (fast_codec and self.threads >= 4) else "dense"
+        self.transport = transport if returns == "obs" else ("packed" if returns == "packed" else "dense")
         dev = env.engine.device.index
         b = env.batch_size
         self.actions = hostmem.pinned_empty((b,), torch.int32, dev)
@@ -198,10 +219,14 @@ class HostStepper(object):
         self.reward = self._tail[:4 * b].view(torch.float32)
         self.done = self._tail[4 * b:]
         self.obs = hostmem.pinned_empty(tuple(env.obs.shape), env.obs_dtype, dev) if returns == "obs" else None
-        self.rec = hostmem.pinned_empty(tuple(env.rec.shape), torch.uint8, dev) if returns == "packed" else None
+        self.rec = hostmem.pinned_empty(tuple(env.rec.shape), torch.uint8, dev) if self.transport == "packed" else None
+        self._obs_over_pcie = self.obs is not None and self.transport == "dense"
         self.h2d_bytes = self.actions.numel() * 4
-        self.d2h_bytes = self._tail.numel() + (self.obs.numel() * self.obs.element_size() if self.obs is not None else 0) \
+        self.d2h_bytes = self._tail.numel() + (self.obs.numel() * self.obs.element_size() if self._obs_over_pcie else 0) \
             + (self.rec.numel() if self.rec is not None else 0)
+        self.host_expanded_bytes = self.obs.numel() * self.obs.element_size() if (self.obs is not None
+                                                                                   and not self._obs_over_pcie) else 0
+        self._gg_dtype = _TORCH2GG[env.obs_dtype]
         self._stream = torch.cuda.Stream(device=env.engine.device)
         self.follow_current_stream = bool(follow_current_stream)
         self._graph = None
@@ -211,8 +236,8 @@ class HostStepper(object):
     def _enqueue(self):
         env = self.env
         env._step_actions.copy_(self.actions, non_blocking=True)
-        env._enqueue_step(self.auto_reset)
-        if self.obs is not None:
+        env._enqueue_step(self.auto_reset, want_obs=not self.host_expanded_bytes)
+        if self._obs_over_pcie:
             self.obs.copy_(env.obs, non_blocking=True)
         if self.rec is not None:
             self.rec.copy_(env.rec, non_blocking=True)
@@ -238,18 +263,23 @@ class HostStepper(object):
             else:
                 self._enqueue()
         self._stream.synchronize()
+        if self.host_expanded_bytes:                                 # records arrived: expand them next to the CPU
+            rc = env.engine.lib.gg_host_unpack(self.rec.data_ptr(), env.batch_size, env.size, self._gg_dtype,
+                                               self.obs.data_ptr(), self.threads)
+            if rc:
+                _cabi.check(rc)
         first = self.obs if self.returns == "obs" else (self.rec if self.returns == "packed" else None)
         return first, self.reward, self.done
 
     def expand(self, out=None, dtype=torch.float32, threads=0):
         """packed records of the last step -> dense [B,6,N,N] on the HOST (gg_host_unpack; threads=0: all usable cores)"""
         if self.rec is None:
-            raise ValueError("expand() needs returns='packed'")
+            raise ValueError("expand() needs returns='packed' or transport='packed'")
         env = self.env
         if out is None:
             out = torch.empty((env.batch_size, 6, env.size, env.size), dtype=dtype)
         if out.device.type != "cpu" or not out.is_contiguous() or tuple(out.shape) != (env.batch_size, 6, env.size, env.size):
             raise ValueError("out must be a contiguous host tensor of shape [B,6,N,N]")
         _cabi.check(env.engine.lib.gg_host_unpack(self.rec.data_ptr(), env.batch_size, env.size, _TORCH2GG[out.dtype],
-                                                  out.data_ptr(), int(threads)))
+                                                  out.data_ptr(), int(threads) if threads and threads > 0 else self.threads))
         return out

@@ -114,6 +114,28 @@ def bind_thread_near(device_index):
     return len(want)
 
 
+def usable_cores():
+    """host threads this process may really use: affinity mask capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = (_read("/sys/fs/cgroup/cpu.max") or "max").split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
+def codec_threads():
+    """default thread count of the host codec for THIS process: the usable cores shared out over the ranks torchrun
+    started on this node (LOCAL_WORLD_SIZE), so that one process per GPU does not oversubscribe the host"""
+    try:
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        ranks = 1
+    return max(1, usable_cores() // ranks)
+
+
 def pinned_empty(shape, dtype, device_index=None):
     """pinned host tensor, its pages preferably on the NUMA node of CUDA device `device_index`"""
     node = None if device_index is None else gpu_numa_node(device_index)

@@ -216,10 +216,15 @@ GG_API int gg_symmetry(const void *rec_in, void *rec_out, int64_t batch, int n, 
 GG_API int gg_probe_write(void *buf, int64_t bytes, int64_t run_bytes, void *stream);
 
 /* HOST codec (the only entry point that takes host pointers and runs on the CPU): packed records in host memory ->
- * dense [B,6,N,N] of dtype in host memory, `threads` worker threads (<= 0: all hardware threads, capped at 64).
- * For consumers that fetch the packed records over PCIe instead of the 40x larger dense observation
- * (BatchedGoEnv.host_stepper(returns="packed")).  No Go rules run here - it is gg_unpack's layout, nothing else. */
+ * dense [B,6,N,N] of dtype in host memory, `threads` worker threads (<= 0: all hardware threads, capped at 64) taken
+ * from a persistent pool.  For consumers that fetch the packed records over PCIe instead of the 40x larger dense
+ * observation (BatchedGoEnv.host_stepper(transport="packed")): with AVX-512 (mask moves + non-temporal stores, chosen
+ * at run time) the expansion runs at host-memory write speed, which beats the PCIe transfer of the dense tensor.
+ * A 64-byte aligned `dense_host` gets the streaming-store path.  Calls are serialised inside the library.
+ * No Go rules run here - it is gg_unpack's layout, nothing else. */
 GG_API int gg_host_unpack(const void *rec_host, int64_t batch, int n, int dtype, void *dense_host, int threads);
+/* which implementation gg_host_unpack runs on this CPU ("avx512 ..." or "scalar") */
+GG_API const char *gg_host_unpack_path(void);
 
 #ifdef __cplusplus
 }

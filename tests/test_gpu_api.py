@@ -250,7 +250,7 @@ def test_host_stepper_matches_device_step(returns, graph):
     from gymgo_b200.envs import BatchedGoEnv
     env = BatchedGoEnv(3000, 9, reward_method="heuristic", komi=0.5, obs_dtype=torch.float32)
     ref = BatchedGoEnv(3000, 9, reward_method="heuristic", komi=0.5, obs_dtype=torch.float32)
-    hs = env.host_stepper(returns=returns, use_cuda_graph=graph)
+    hs = env.host_stepper(returns=returns, use_cuda_graph=graph, transport="dense")
     assert hs.h2d_bytes == 3000 * 4
     assert hs.d2h_bytes == 3000 * 5 + {"obs": 3000 * 6 * 81 * 4, "packed": 3000 * env.engine.rec_bytes, "none": 0}[returns]
     for t in range(140):
@@ -267,6 +267,30 @@ def test_host_stepper_matches_device_step(returns, graph):
             assert torch.equal(hs.expand(), o.cpu())
             assert torch.equal(hs.expand(dtype=torch.uint8, threads=3), o.cpu().to(torch.uint8))
     assert torch.equal(env.rec, ref.rec) and bool(ref.done.any())
+
+
+@pytest.mark.parametrize("n,dtype", ((9, torch.float32), (19, torch.float32), (9, torch.bfloat16), (7, torch.uint8)))
+def test_host_stepper_packed_transport_returns_the_same_observation(n, dtype):
+    """host_stepper(transport="packed"): records over PCIe + gg_host_unpack on the host cores == the dense observation the
+    kernel writes (transport="dense"), bit for bit, with 40x fewer bytes crossing the bus"""
+    from gymgo_b200.envs import BatchedGoEnv
+    b = 2500                                                        # ragged: not a multiple of the codec's 32-board chunk
+    env = BatchedGoEnv(b, n, obs_dtype=dtype)
+    ref = BatchedGoEnv(b, n, obs_dtype=dtype)
+    hs = env.host_stepper(returns="obs", transport="packed", threads=3)
+    assert hs.d2h_bytes == b * 5 + b * env.engine.rec_bytes and hs.host_expanded_bytes == b * 6 * n * n * env.obs.element_size()
+    for t in range(60):
+        acts = ref.engine.sample_legal(ref.rec, 4, 0, t)
+        hs.actions.copy_(acts.cpu())
+        obs, rew, done = hs.step()
+        o, r, d, _ = ref.step(acts, auto_reset=True)
+        assert not obs.is_cuda and obs.dtype == dtype
+        assert torch.equal(obs, o.cpu()) and torch.equal(rew, r.cpu()) and torch.equal(done, d.cpu())
+    assert torch.equal(env.rec, ref.rec)
+    auto = env.host_stepper(returns="obs")                           # the default picks one of the two, never anything else
+    assert auto.transport in ("dense", "packed") and env.host_stepper(returns="none").transport == "dense"
+    with pytest.raises(ValueError):
+        env.host_stepper(returns="obs", transport="carrier pigeon")
 
 
 @pytest.mark.parametrize("n", (5, 9, 13, 19))
