@@ -750,6 +750,60 @@ struct TpbTile {
     static constexpr int WSTREAM_W32 = (32 * DENSE + 15 + 31) / 32 + 2;
 };
 
+// Bit stream of a thread-per-board warp WITHOUT shared-memory atomics: every thread assembles the 6*N*N dense bits of
+// its board in registers (all offsets inside a board are compile-time constants), shifts them to the board's position
+// in the warp stream with funnel shifts, and stores whole words.  The one word a board shares with its successor is
+// merged through a shuffle and stored by the lower lane, so no word is written twice and nothing needs zeroing.
+template <class G>
+struct TpbStream {
+    static constexpr int DENSE = 6 * G::NP;
+    static constexpr int KW = (DENSE + 31) / 32;                 // words of one board's bits before shifting
+    // uint32 boards whose stream words hold bits of at most two boards; the rest keeps the atomicOr stream
+    static constexpr bool SHUFFLED = DENSE >= 64 && G::WB == 32;
+};
+template <class G>
+__device__ __forceinline__ void tpb_stream_put(uint32_t* s_bits, int off, int lane, bool real, const ArrayPlane<G>& black,
+                                               const ArrayPlane<G>& white, const ArrayPlane<G>& invd, uint32_t flags) {
+    typedef TpbStream<G> TS;
+    constexpr int KW = TS::KW;
+    uint32_t L[KW];
+#pragma unroll
+    for (int k = 0; k < KW; ++k) L[k] = 0;
+#pragma unroll
+    for (int ch = 0; ch < 6; ++ch) {
+#pragma unroll
+        for (int j = 0; j < G::LPB; ++j) {
+            const int rows = G::N - j * G::RPL < G::RPL ? G::N - j * G::RPL : G::RPL;    // compile-time after unrolling
+            if (rows <= 0) continue;
+            const int nbits = rows * G::N, at = ch * G::NP + j * G::RPL * G::N;
+            uint32_t v;
+            if (ch == 0) v = uint32_t(compact_rows<G>(black.w[j]));
+            else if (ch == 1) v = uint32_t(compact_rows<G>(white.w[j]));
+            else if (ch == 3) v = uint32_t(compact_rows<G>(invd.w[j]));
+            else v = (flags & (ch == 2 ? FLAG_TURN : (ch == 4 ? FLAG_PASS : FLAG_DONE))) ? ((1u << nbits) - 1u) : 0u;
+            L[at >> 5] |= v << (at & 31);
+            if ((at & 31) + nbits > 32) L[(at >> 5) + 1] |= v >> (32 - (at & 31));
+        }
+    }
+    const int sh = off & 31, w0 = off >> 5;
+    const int last = (sh + TS::DENSE - 1) >> 5;                    // index (from w0) of my last word: KW - 1 or KW
+    const bool tail_partial = ((sh + TS::DENSE) & 31) != 0;        // ... which I share with the next board
+    // word k of my shifted stream = funnel(L[k-1], L[k]); my first word's low `sh` bits belong to the previous board
+    const uint32_t first = L[0] << sh;
+    const uint32_t next_first = __shfl_down_sync(0xffffffffu, first, 1);      // lanes without a board carry zeros
+    const uint32_t merge = (tail_partial && lane < 31) ? next_first : 0u;
+    if (!real) return;
+    uint32_t* dst = s_bits + w0;
+    if (sh == 0 || lane == 0) dst[0] = first;                      // otherwise the previous lane stores this word
+#pragma unroll
+    for (int k = 1; k < KW - 1; ++k) dst[k] = __funnelshift_l(L[k - 1], L[k], sh);
+    {
+        const uint32_t wa = __funnelshift_l(L[KW - 2], L[KW - 1], sh);
+        dst[KW - 1] = last == KW - 1 ? (wa | merge) : wa;
+        if (last == KW) dst[KW] = __funnelshift_l(L[KW - 1], 0u, sh) | merge;
+    }
+}
+
 template <class G>
 __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k_rollout_tpb(const RolloutArgs a) {
     typedef typename G::W W;
@@ -839,17 +893,20 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
             const long long abs0 = (long long)(t % (unsigned long long)a.ring) * slot_elems + e0;
             const int head = int(abs0 & align_mask);
             const long long at = abs0 - head;
-            __syncwarp();
-            for (int i = lane; i < T::WSTREAM_W32; i += 32) s_bits[i] = 0;
-            __syncwarp();
-            if (real) {
+            __syncwarp();                                          // the previous ply's expansion has read the stream
+            if constexpr (TpbStream<G>::SHUFFLED) {
+                tpb_stream_put<G>(s_bits, head + lane * T::DENSE, lane, real, black, white, invd, flags);
+            } else {
+                for (int i = lane; i < T::WSTREAM_W32; i += 32) s_bits[i] = 0;
+                __syncwarp();
+                if (real) {
 #pragma unroll
-                for (int j = 0; j < G::LPB; ++j)
-                    stream_put_board<G>(s_bits, head + lane * T::DENSE, j, black.w[j], white.w[j], invd.w[j], flags);
+                    for (int j = 0; j < G::LPB; ++j)
+                        stream_put_board<G>(s_bits, head + lane * T::DENSE, j, black.w[j], white.w[j], invd.w[j], flags);
+                }
             }
             __syncwarp();
             emit_obs<32>(a.obs_dtype, s_bits, s_lut, head, count, a.obs_ring, at, lane);
-            __syncwarp();
         }
     }
 

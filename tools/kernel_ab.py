@@ -31,7 +31,12 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_ab.json"))
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--ppl", type=int, default=32)
+    ap.add_argument("--lib", default=None, help="developer A/B: load this build of libgymgo_b200.so instead of the in-tree one")
     args = ap.parse_args()
+    if args.lib:
+        from gymgo_b200 import build as _b
+        _b.LIB = os.path.abspath(args.lib)
+        _b.up_to_date = lambda: True
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:  # noqa: BLE001
