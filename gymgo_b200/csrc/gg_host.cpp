@@ -28,8 +28,11 @@ namespace gg {
 namespace {
 
 // ------------------------------------------------------------------------------------------ worker pool
-// Persistent threads (created on first use, grown on demand, never joined: the library has no tear-down entry point
-// and the threads sleep on a condition variable).  One job at a time; callers serialise on `run_mu`.
+// Persistent threads (created on first use, grown on demand, never joined: the library has no tear-down entry point).
+// One job at a time (callers serialise on run_mu_).  A job is finished when all its ITEMS are done - not when every
+// helper has reported - so a helper that wakes up late costs nothing: the caller and the punctual helpers take its
+// share.  Tickets carry the job's epoch, so a late helper can never take an item of a later job with a stale snapshot.
+// Helpers poll for ~0.5 ms after a job before they block: a stepping loop calls again within that time.
 class Pool {
   public:
     void run(int workers, int64_t items, const std::function<void(int64_t)>& fn) {
@@ -38,53 +41,74 @@ class Pool {
             for (int64_t i = 0; i < items; ++i) fn(i);
             return;
         }
+        Job job;
         {
-            std::unique_lock<std::mutex> lk(mu_);
+            std::lock_guard<std::mutex> lk(mu_);
             while (int(threads_.size()) < workers - 1) threads_.emplace_back([this, id = int(threads_.size())] { loop(id); });
-            fn_ = &fn;
-            items_ = items;
-            next_.store(0, std::memory_order_relaxed);
-            helpers_ = workers - 1;
-            pending_ = workers - 1;
-            ++epoch_;
+            job.fn = &fn;
+            job.items = items;
+            job.helpers = workers - 1;
+            job.epoch = job_.epoch + 1;
+            job_ = job;
+            done_.store(0, std::memory_order_relaxed);
+            next_.store((job.epoch & EPOCH_MASK) << INDEX_BITS, std::memory_order_relaxed);
+            epoch_.store(job.epoch, std::memory_order_release);    // helpers that are still polling start right away
         }
-        cv_.notify_all();
-        drain();
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [this] { return pending_ == 0; });
-        fn_ = nullptr;
+        cv_.notify_all();                                          // ... the ones that went to sleep are woken
+        work(job);
+        for (int spin = 0; done_.load(std::memory_order_acquire) != items; ++spin) {   // items in flight elsewhere
+            if (spin < 4096) _mm_pause();
+            else std::this_thread::yield();
+        }
     }
 
   private:
-    void drain() {
+    struct Job {
+        const std::function<void(int64_t)>* fn = nullptr;
+        int64_t items = 0;
+        int helpers = 0;
+        uint64_t epoch = 0;
+    };
+    static constexpr int INDEX_BITS = 40;
+    static constexpr uint64_t INDEX_MASK = (uint64_t(1) << INDEX_BITS) - 1, EPOCH_MASK = (uint64_t(1) << 24) - 1;
+    static constexpr int SPIN_ROUNDS = 1 << 15;                    // ~0.5 ms of polling before a helper blocks
+
+    void work(const Job& j) {
+        uint64_t v = next_.load(std::memory_order_relaxed);
         for (;;) {
-            const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
-            if (i >= items_) break;
-            (*fn_)(i);
+            if ((v >> INDEX_BITS) != (j.epoch & EPOCH_MASK) || int64_t(v & INDEX_MASK) >= j.items) return;
+            if (!next_.compare_exchange_weak(v, v + 1, std::memory_order_relaxed)) continue;      // v reloaded
+            (*j.fn)(int64_t(v & INDEX_MASK));                      // the caller waits for this item: fn is alive
+            done_.fetch_add(1, std::memory_order_release);
+            v = next_.load(std::memory_order_relaxed);
         }
     }
     void loop(int id) {
         uint64_t seen = 0;
+        bool took_part = false;                                    // only helpers of the last job poll for the next one
         for (;;) {
+            bool got = false;
+            for (int spin = 0; took_part && spin < SPIN_ROUNDS && !got; ++spin) {
+                got = epoch_.load(std::memory_order_acquire) != seen;
+                if (!got) _mm_pause();
+            }
+            Job j;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return epoch_ != seen; });
-                seen = epoch_;
-                if (id >= helpers_) continue;              // this job wants fewer workers than the pool holds
+                if (!got) cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+                j = job_;                                          // published under this lock
             }
-            drain();
-            std::unique_lock<std::mutex> lk(mu_);
-            if (--pending_ == 0) done_cv_.notify_one();
+            seen = j.epoch;
+            took_part = id < j.helpers;                            // else: this job wants fewer workers than the pool holds
+            if (took_part) work(j);
         }
     }
     std::mutex run_mu_, mu_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
     std::vector<std::thread> threads_;
-    const std::function<void(int64_t)>* fn_ = nullptr;
-    std::atomic<int64_t> next_{0};
-    int64_t items_ = 0;
-    int helpers_ = 0, pending_ = 0;
-    uint64_t epoch_ = 0;
+    Job job_;
+    std::atomic<uint64_t> next_{0}, epoch_{0};
+    std::atomic<int64_t> done_{0};
 };
 Pool& pool() {
     static Pool* p = new Pool;                              // leaked on purpose (threads outlive static destructors)
@@ -287,8 +311,9 @@ void host_unpack(const uint8_t* rec, int64_t batch, int n, int lpb, int rpl, int
     const bool nt = simd && (reinterpret_cast<uintptr_t>(dense) & 63u) == 0;     // chunk strides keep the alignment
     const size_t chunk_out_bytes = size_t(CHUNK) * 6 * g.np * size_t(elem_bytes(dtype));
     const int64_t chunks = (batch + CHUNK - 1) / CHUNK;
-    // a work item = a run of chunks (amortises the ticket and keeps each thread's output contiguous for a while)
-    const int64_t run = 16;
+    // a work item = a run of chunks worth >= 256 KB of output: fine enough that a late worker costs little (an item
+    // is ~25 us of streaming stores), coarse enough that the ticket is free
+    const int64_t run = chunk_out_bytes >= (256u << 10) ? 1 : int64_t((256u << 10) / chunk_out_bytes);
     const int64_t items = (chunks + run - 1) / run;
     const std::function<void(int64_t)> job = [&](int64_t item) {
         const int64_t c0 = item * run, c1 = c0 + run < chunks ? c0 + run : chunks;

@@ -88,6 +88,43 @@ def test_host_codec_matches_the_record_layout():
         assert np.array_equal(half, st.astype(np.uint16) * 0x3F80)
 
 
+def test_host_codec_pool_is_safe_under_concurrent_callers_and_odd_shapes():
+    """the codec's persistent worker pool: concurrent callers are serialised inside the library, thread counts above the
+    work-item count and batches below one chunk work, and a misaligned destination takes the unaligned-store path"""
+    import threading
+    import numpy as np
+    import hostsim
+    from gymgo_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.gg_host_unpack_path().decode().split()[0] in ("avx512", "scalar")
+    n = 9
+    rng = np.random.RandomState(5)
+    st = (rng.uniform(size=(9000, 6, n, n)) < 0.3).astype(np.uint8)
+    st[:, [2, 4, 5]] = rng.randint(2, size=(9000, 3))[:, :, None, None]
+    rec = np.ascontiguousarray(hostsim.pack(st)).view(np.uint8)
+    outs = [np.empty((9000, 6, n, n), dtype=np.float32) for _ in range(4)]
+    errs = []
+
+    def work(k):
+        for _ in range(5):
+            if lib.gg_host_unpack(rec.ctypes.data, 9000, n, _cabi.GG_F32, outs[k].ctypes.data, 2 + k) != 0:
+                errs.append(k)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs and all(np.array_equal(o, st.astype(np.float32)) for o in outs)
+    for batch in (0, 1, 31, 33):                                         # below / around one 32-board chunk, 64 threads asked
+        out = np.full((max(batch, 1), 6, n, n), 7, dtype=np.float16)
+        assert lib.gg_host_unpack(rec.ctypes.data, batch, n, _cabi.GG_F16, out.ctypes.data, 64) == 0
+        assert np.array_equal(out[:batch].view(np.uint16), st[:batch].astype(np.uint16) * 0x3C00)
+    raw = np.empty(9000 * 6 * n * n * 8 + 64, dtype=np.uint8)            # float64, destination off by 8 bytes from 64
+    off = (-raw.ctypes.data) % 64 + 8
+    dst = raw[off:off + 9000 * 6 * n * n * 8].view(np.float64).reshape(9000, 6, n, n)
+    assert lib.gg_host_unpack(rec.ctypes.data, 9000, n, _cabi.GG_F64, dst.ctypes.data, 3) == 0
+    assert np.array_equal(dst, st.astype(np.float64))
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
