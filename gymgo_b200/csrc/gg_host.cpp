@@ -32,7 +32,8 @@ namespace {
 // One job at a time (callers serialise on run_mu_).  A job is finished when all its ITEMS are done - not when every
 // helper has reported - so a helper that wakes up late costs nothing: the caller and the punctual helpers take its
 // share.  Tickets carry the job's epoch, so a late helper can never take an item of a later job with a stale snapshot.
-// Helpers poll for ~0.5 ms after a job before they block: a stepping loop calls again within that time.
+// Helpers block on a condition variable between jobs: polling for the next job was measured and bought nothing in a
+// stepping loop while it slowed every other host thread down (profiles/r02_host_codec_probe.json).
 class Pool {
   public:
     void run(int workers, int64_t items, const std::function<void(int64_t)>& fn) {
@@ -52,9 +53,9 @@ class Pool {
             job_ = job;
             done_.store(0, std::memory_order_relaxed);
             next_.store((job.epoch & EPOCH_MASK) << INDEX_BITS, std::memory_order_relaxed);
-            epoch_.store(job.epoch, std::memory_order_release);    // helpers that are still polling start right away
+            epoch_.store(job.epoch, std::memory_order_release);
         }
-        cv_.notify_all();                                          // ... the ones that went to sleep are woken
+        cv_.notify_all();
         work(job);
         for (int spin = 0; done_.load(std::memory_order_acquire) != items; ++spin) {   // items in flight elsewhere
             if (spin < 4096) _mm_pause();
@@ -71,7 +72,6 @@ class Pool {
     };
     static constexpr int INDEX_BITS = 40;
     static constexpr uint64_t INDEX_MASK = (uint64_t(1) << INDEX_BITS) - 1, EPOCH_MASK = (uint64_t(1) << 24) - 1;
-    static constexpr int SPIN_ROUNDS = 1 << 15;                    // ~0.5 ms of polling before a helper blocks
 
     void work(const Job& j) {
         uint64_t v = next_.load(std::memory_order_relaxed);
@@ -85,22 +85,15 @@ class Pool {
     }
     void loop(int id) {
         uint64_t seen = 0;
-        bool took_part = false;                                    // only helpers of the last job poll for the next one
         for (;;) {
-            bool got = false;
-            for (int spin = 0; took_part && spin < SPIN_ROUNDS && !got; ++spin) {
-                got = epoch_.load(std::memory_order_acquire) != seen;
-                if (!got) _mm_pause();
-            }
             Job j;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                if (!got) cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+                cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
                 j = job_;                                          // published under this lock
             }
             seen = j.epoch;
-            took_part = id < j.helpers;                            // else: this job wants fewer workers than the pool holds
-            if (took_part) work(j);
+            if (id < j.helpers) work(j);                           // else: this job wants fewer workers than the pool holds
         }
     }
     std::mutex run_mu_, mu_;
