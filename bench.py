@@ -124,7 +124,7 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def _cpu_worker(size, boards, warmup, steps, seed, barrier, out_q):
+def _cpu_worker(size, boards, preroll, warmup, steps, repeats, seed, barrier, out_q):
     os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
     from oracle import gogame_np as og
@@ -138,11 +138,11 @@ def _cpu_worker(size, boards, warmup, steps, seed, barrier, out_q):
             s = og.next_state(s, a)
             states[i] = og.init_state(size) if og.game_ended(s) else s
 
-    for _ in range(warmup):
+    for _ in range(preroll + warmup):          # same untimed set-up as the GPU arm: game phases de-synchronised
         ply()
     barrier.wait()
     t0 = time.time()
-    for _ in range(steps):
+    for _ in range(steps * repeats):
         ply()
     out_q.put(time.time() - t0)
 
@@ -159,12 +159,14 @@ def usable_cores():
     return n
 
 
-def cpu_reference_run(size, boards_per_core, warmup, steps, cores=None):
-    """every host core steps `boards_per_core` boards with the numpy/scipy port; -> (plies/s, cores, seconds)"""
+def cpu_reference_run(size, boards_per_core, warmup, steps, cores=None, preroll=PREROLL, repeats=1):
+    """every host core steps `boards_per_core` boards with the numpy/scipy port, after `preroll` untimed set-up plies
+    (the GPU arm's steady-state definition); the timed region is `repeats` x `steps` plies, like the GPU arm's;
+    -> (plies/s, cores, seconds)"""
     cores = cores or usable_cores()
     ctx = mp.get_context("fork")
     barrier, q = ctx.Barrier(cores), ctx.Queue()
-    procs = [ctx.Process(target=_cpu_worker, args=(size, boards_per_core, warmup, steps, 100 + i, barrier, q))
+    procs = [ctx.Process(target=_cpu_worker, args=(size, boards_per_core, preroll, warmup, steps, repeats, 100 + i, barrier, q))
              for i in range(cores)]
     for p in procs:
         p.start()
@@ -172,7 +174,7 @@ def cpu_reference_run(size, boards_per_core, warmup, steps, cores=None):
     for p in procs:
         p.join()
     secs = max(times)
-    return cores * boards_per_core * steps / secs, cores, secs
+    return cores * boards_per_core * steps * repeats / secs, cores, secs
 
 
 def c_oracle_rate(size, seconds=2.0):
@@ -198,14 +200,18 @@ def run_reference(args, wl, rank, world):
     max_steps = int(budget_s * rate / boards_per_core)
     steps = min(args.steps, max(1, int(max_steps * args.steps / float(args.steps + args.warmup))))
     warmup = min(args.warmup, max(0, max_steps - steps))
-    value, cores, secs = cpu_reference_run(size, boards_per_core, warmup, steps)
-    sample = "%d cores x %d boards x %d plies (after %d warm-up plies), numpy/scipy port of gogame.next_state, " \
-             "uniform-random-legal incl. pass, restart on game end" % (cores, boards_per_core, steps, warmup)
+    # like the GPU arm, the K timed steps are repeated so that the region is long enough to time (~10 s of CPU work)
+    repeats = max(1, int(round(10.0 * rate / (boards_per_core * steps))))
+    value, cores, secs = cpu_reference_run(size, boards_per_core, warmup, steps, repeats=repeats)
+    sample = "%d cores x %d boards x (%d repetitions x %d plies) after %d untimed set-up plies + %d warm-up plies (the " \
+             "GPU arm's steady-state definition), numpy/scipy port of gogame.next_state, uniform-random-legal incl. " \
+             "pass, restart on game end" % (cores, boards_per_core, repeats, steps, PREROLL, warmup)
     line = {
         "impl": "reference", "metric": "env-steps/sec (batched random-legal rollout)", "value": value,
-        "unit": "env-steps/s", "n_gpus": 0, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / steps,
+        "unit": "env-steps/s", "n_gpus": 0, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / (steps * repeats),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "board_size": size, "boards": cores * boards_per_core,
+                   "preroll_plies": PREROLL, "repeats": repeats,
                    "note": "CPU arm: a step = one ply on every board of the bounded sample; kind=port: the reference is "
                            "pure Python with gym/pyglet imports and cannot travel to the GPU box; the port keeps its "
                            "scipy.ndimage arithmetic and ran 1.35-1.5x faster than the unmodified reference in the "
