@@ -380,7 +380,7 @@ def run_ours(args, wl, rank, world, local_rank):
     barrier()
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    write_ceiling = write_ceiling_gbs(eng, main.ring) if rank == 0 else None
+    write_ceiling = write_ceiling_gbs(eng, main.ring) if (rank == 0 and not args.quick) else None
 
     # ---------------- transparency: the same plies with ONE launch per ply (records reloaded and stored every ply)
     n1 = min(max(K, 20), 100)
@@ -625,7 +625,7 @@ def main():
                     help="plies the persistent rollout kernel plays per launch = slots of the observation ring (128 = one "
                          "PPO-style rollout segment per launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="headline + f32 e2e only (no extra configs, no e2e variants)")
+    ap.add_argument("--quick", action="store_true", help="headline + f32 e2e only (no extra configs, no e2e variants, no plain-fill probe)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
