@@ -149,14 +149,16 @@ GG_HD int w_select(uint64_t x, int k) {
 }
 
 // Row flood inside one word: every maximal run of consecutive bits of `m` that contains a bit of
-// `s` (s subset of m) becomes fully set.  (m + s) ripples a carry from each seed to the top of its
-// run and dies in the 0 bit above it (guard bit / word end); the reversed word does the other way.
+// `s` (s subset of m) becomes fully set.  a = m + s ripples a carry from each seed to the top of its run
+// (it dies in the 0 bit above: guard bit / word end), so inside m the bits of a run at and above its lowest seed
+// come out as ~a (except further seeds); the bit-reversed word does the other direction: b = rev(mrev + rev(s)).
+// A run bit is reached iff it is flipped in one of the two sums: m & ~(a & b), plus the seeds themselves (a seed
+// with seeds on both sides is flipped back in both).  Two additions, two reversals, two logic operations.
 template <class W>
 GG_HD W w_hfill(W s, W m, W mrev) {
-    W up = (m + s) ^ m;
-    W sr = w_rev(s);
-    W dn = w_rev(W((mrev + sr) ^ mrev));
-    return ((up | dn) & m) | s;
+    const W a = m + s;
+    const W b = w_rev(W(mrev + w_rev(s)));
+    return (m & ~(a & b)) | s;
 }
 
 // Philox4x32-10 (Salmon et al., SC'11) - counter-based, so a board's random stream depends only on
@@ -178,7 +180,8 @@ GG_HD uint32_t philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 //   typedef P                      plane (device: one word; host: LPB words)
 //   P zero(), full()               empty plane / all real points of this board
 //   P east(P) west(P)              1-column moves   (result must still be masked with full())
-//   P south(P) north(P)            1-row moves      (south: result[r] = x[r-1]; north: x[r+1])
+//   P south(P) north(P)            1-row moves      (south: result[r] = x[r-1]; north: x[r+1]; may leave bits above
+//                                  the word's row slots: like east/west, mask the result with full() or a plane)
 //   P rev(P), hfill(s, m, mrev)    per-word bit reversal / row flood
 //   bool any(P)                    LOOP CONTROL ONLY: true if any board sharing my warp has a bit
 //   bool any_board(P)              this board has a bit

@@ -81,7 +81,8 @@ struct ArrayOps {
         P y;
         GG_UNROLL for (int j = 0; j < G::LPB; ++j) {
             const W in = G::RPL > 1 ? W(x.w[j] >> (G::S % G::WB)) : W(0);
-            const W next = j + 1 < G::LPB ? W((x.w[j + 1 < G::LPB ? j + 1 : j] & G::row_bits()) << ((G::RPL - 1) * G::S)) : W(0);
+            // (rows 1.. of the next word land above the RPL row slots: outside every mask, like south's top row)
+            const W next = j + 1 < G::LPB ? W(x.w[j + 1 < G::LPB ? j + 1 : j] << ((G::RPL - 1) * G::S)) : W(0);
             y.w[j] = in | next;
         }
         return y;

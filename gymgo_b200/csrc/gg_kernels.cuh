@@ -130,7 +130,7 @@ struct DevOps {
         if (G::RPL > 1) r = x >> (G::S % G::WB);
         if (G::LPB > 1) {
             const W next = __shfl_down_sync(FULL, x, 1);
-            if (j < G::LPB - 1) r |= (next & G::row_bits()) << ((G::RPL - 1) * G::S);
+            if (j < G::LPB - 1) r |= next << ((G::RPL - 1) * G::S);   // (its rows 1.. land above the RPL row slots)
         }
         return r;
     }
