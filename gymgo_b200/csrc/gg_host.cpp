@@ -110,27 +110,37 @@ Pool& pool() {
 
 // ------------------------------------------------------------------------------------------ bit stream of a chunk
 constexpr int CHUNK = 32;                                   // boards per chunk: 32 * 6 * N*N bits = 3*N*N whole words
-constexpr int MAX_WORDS = 3 * 19 * 19 + 2;
+constexpr int MAX_WORDS = 3 * 19 * 19 + 3;
 
 struct Geo {
     int n, np, s, lpb, rpl, word_bytes, plane_bytes, rec_bytes;
     uint64_t rows_mask[8];                                  // mask of the real points of a word holding 0..7 rows (rpl <= 5)
 };
 
-inline void put(uint64_t* s, size_t& off, uint64_t v, int nbits) {     // v has no bits at or above nbits
-    const size_t w = off >> 6;
-    const int sh = int(off & 63);
-    s[w] |= v << sh;
-    if (sh + nbits > 64) s[w + 1] |= v >> (64 - sh);
-    off += size_t(nbits);
-}
-inline void put_ones(uint64_t* s, size_t& off, int nbits) {
-    while (nbits >= 64) {
-        put(s, off, ~uint64_t(0), 64);
-        nbits -= 64;
+// Bit appender that keeps the word under construction in a register (no read-modify-write chain through memory) and
+// is branch-free: every append stores the current word (it is simply stored again until it is full) and steps to
+// the next one when it fills up; finish() stores the last, partial word.  The spill into the next word is (v >> 1) >> (63 - fill): 0 when nothing spills.
+struct BitSink {
+    uint64_t* out;
+    uint64_t acc = 0;
+    int fill = 0;
+    explicit BitSink(uint64_t* o) : out(o) {}
+    inline void put(uint64_t v, int nbits) {                       // 1 <= nbits <= 64, no bits of v at or above nbits
+        acc |= v << fill;
+        *out = acc;
+        const int nf = fill + nbits;
+        const bool wrap = nf >= 64;
+        const uint64_t spill = (v >> 1) >> (63 - fill);
+        acc = wrap ? spill : acc;
+        out += wrap;
+        fill = nf & 63;
     }
-    if (nbits) put(s, off, (uint64_t(1) << nbits) - 1, nbits);
-}
+    inline void finish() { *out = acc; }                           // the word under construction (stream has a spare word)
+    inline void put_run(uint64_t on, int nbits) {                  // nbits copies of one bit (on = 0 or ~0)
+        for (; nbits >= 64; nbits -= 64) put(on, 64);
+        if (nbits) put(on & ((uint64_t(1) << nbits) - 1), nbits);
+    }
+};
 inline uint64_t compact_scalar(uint64_t w, int rows, int n, int s) {
     uint64_t out = 0;
     const uint64_t row = (uint64_t(1) << n) - 1;
@@ -145,36 +155,37 @@ inline uint64_t pext64(uint64_t w, uint64_t mask) {
     return out;
 }
 
-template <bool BMI2>
+// WORD = uint32_t / uint64_t: the record's word type (fixed-size loads instead of a run-time memcpy length)
+template <bool BMI2, class WORD>
 inline void chunk_bits(const Geo& g, const uint8_t* rec, int boards, uint64_t* stream) {
-    memset(stream, 0, sizeof(uint64_t) * size_t((size_t(boards) * 6 * g.np + 63) / 64 + 1));
-    size_t off = 0;
+    BitSink sink(stream);
+    const int full_words = g.n / g.rpl, tail_rows = g.n - full_words * g.rpl;      // words holding rpl rows, rows of the last
+    const uint64_t full_mask = g.rows_mask[g.rpl], tail_mask = g.rows_mask[tail_rows];
+    const int full_bits = g.rpl * g.n, tail_bits = tail_rows * g.n;
     for (int b = 0; b < boards; ++b) {
         const uint8_t* r = rec + size_t(b) * g.rec_bytes;
         uint32_t flags;
         memcpy(&flags, r + 3 * g.plane_bytes, 4);
         for (int ch = 0; ch < 6; ++ch) {
             if (ch == 2 || ch == 4 || ch == 5) {            // constant planes: turn / previous pass / game over
-                const uint32_t bit = ch == 2 ? 1u : (ch == 4 ? 2u : 4u);
-                if (flags & bit) put_ones(stream, off, g.np);
-                else off += size_t(g.np);
+                const int bit = ch == 2 ? 0 : (ch == 4 ? 1 : 2);
+                sink.put_run(uint64_t(0) - uint64_t((flags >> bit) & 1u), g.np);
                 continue;
             }
             const uint8_t* plane = r + (ch == 3 ? 2 : ch) * g.plane_bytes;
-            int rows_left = g.n;
-            for (int j = 0; j < g.lpb; ++j) {
-                const int rows = rows_left < g.rpl ? rows_left : g.rpl;
-                rows_left -= rows;
-                if (rows <= 0) break;
-                uint64_t w = 0;
-                memcpy(&w, plane + j * g.word_bytes, size_t(g.word_bytes));
-                uint64_t bits;
-                if (BMI2) bits = pext64(w, g.rows_mask[rows]);
-                else bits = compact_scalar(w, rows, g.n, g.s);
-                put(stream, off, bits, rows * g.n);
+            for (int j = 0; j < full_words; ++j) {
+                WORD w;
+                memcpy(&w, plane + j * sizeof(WORD), sizeof(WORD));
+                sink.put(BMI2 ? pext64(w, full_mask) : compact_scalar(w, g.rpl, g.n, g.s), full_bits);
+            }
+            if (tail_rows) {
+                WORD w;
+                memcpy(&w, plane + full_words * sizeof(WORD), sizeof(WORD));
+                sink.put(BMI2 ? pext64(w, tail_mask) : compact_scalar(w, tail_rows, g.n, g.s), tail_bits);
             }
         }
     }
+    sink.finish();
 }
 
 // ------------------------------------------------------------------------------------------ expansion
@@ -256,8 +267,8 @@ int elem_bytes(int dtype) { return dtype == HOST_U8 ? 1 : (dtype == HOST_F32 ? 4
 void do_chunk(const Geo& g, const uint8_t* rec, int boards, int dtype, uint16_t one16, void* out, bool simd, bool nt) {
     uint64_t stream[MAX_WORDS];
     const size_t elems = size_t(boards) * 6 * g.np;
-    if (simd) chunk_bits<true>(g, rec, boards, stream);
-    else chunk_bits<false>(g, rec, boards, stream);
+    if (g.word_bytes == 4) simd ? chunk_bits<true, uint32_t>(g, rec, boards, stream) : chunk_bits<false, uint32_t>(g, rec, boards, stream);
+    else simd ? chunk_bits<true, uint64_t>(g, rec, boards, stream) : chunk_bits<false, uint64_t>(g, rec, boards, stream);
     const size_t words = simd ? elems / 64 : 0;             // whole words go through the vector path
     if (words) {
         switch (dtype) {

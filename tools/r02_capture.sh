@@ -17,6 +17,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python bench.py --steps 20 --warmup 5 > $O/bench_9x9_steps20_warmup5.json 2> $O/bench_s20.err
 python bench.py > $O/bench_9x9_default.json 2> $O/bench_default.err
 python bench.py --workload 19x19 --steps 20 --warmup 5 > $O/bench_19x19.json 2> $O/bench_19.err
+for obs in u8 bf16; do
+  python bench.py --obs $obs --steps 20 --warmup 5 --quick --no-cpu-baseline > $O/bench_9x9_$obs.json 2>> $O/bench_s20.err
+  python bench.py --workload 19x19 --obs $obs --steps 20 --warmup 5 --quick --no-cpu-baseline > $O/bench_19x19_$obs.json 2>> $O/bench_s20.err
+done
 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_reference_9x9.json 2>> $O/bench_s20.err
+python bench.py --impl reference --workload 19x19 --steps 20 --warmup 5 > $O/bench_reference_19x19.json 2>> $O/bench_s20.err
+python tools/kernel_ab.py --quick --out $O/kernel_ab_final.json > $O/kernel_ab_final.log 2>&1
+cuobjdump -sass gymgo_b200/_lib/libgymgo_b200.so 2>/dev/null | grep -c ATOMS > $O/atoms_count.txt
 tail -c 300 $O/bench_s20.err $O/bench_default.err $O/bench_19.err
 ls -la $O | tail -20
