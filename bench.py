@@ -456,7 +456,7 @@ def run_ours(args, wl, rank, world, local_rank):
         raise SystemExit("e2e replay diverged from the device rollout - refusing to report")
     if not args.quick:
         legs["f32_dense_over_pcie"] = e2e_leg("obs", obs_dtype, transport="dense")
-        legs["u8"] = e2e_leg("obs", torch.uint8, transport="dense")
+        legs["u8"] = e2e_leg("obs", torch.uint8, transport="auto")
         legs["packed"] = e2e_leg("packed", obs_dtype)
         legs["obs_kept_on_device"] = e2e_leg("none", obs_dtype)
         legs["device_policy"] = device_policy_leg()
@@ -530,7 +530,7 @@ def run_ours(args, wl, rank, world, local_rank):
             e2e["variants"] = {
                 "f32_dense_over_pcie": leg_record("f32_dense_over_pcie", "host_stepper(returns='obs', transport='dense'): the "
                                                   "dense f32 tensor is written on the device and crosses PCIe (round 1's e2e)"),
-                "u8_observation": leg_record("u8", "transport='dense' with obs_dtype=uint8"),
+                "u8_observation": leg_record("u8", "the default call with obs_dtype=uint8 [transport -> '%s']" % legs["u8"]["transport"]),
                 "packed_records": leg_record("packed", "host_stepper(returns='packed'): the packed records only, no dense "
                                                        "tensor anywhere"),
                 "obs_kept_on_device": leg_record("obs_kept_on_device", "host_stepper(returns='none'): host actions in, "
