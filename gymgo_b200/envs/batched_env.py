@@ -193,7 +193,8 @@ class HostStepper(object):
                       "dense".  Measured on the B200 boxes (profiles/r02_host_codec_probe.json): 16 threads expand at
                       180 GB/s of dense output, 4 threads at 53 GB/s, the dense tensor crosses PCIe at 55 GB/s on one
                       GPU and 12 GB/s per GPU when eight GPUs share the host.
-             All return bit-identical tensors.  The codec's workers want the host cores to themselves: a caller whose
+             All return bit-identical tensors (with "packed" the device-side `env.obs` is not refreshed: the consumer is
+             on the host; `env.state()` unpacks on the device when needed).  The codec's workers want the host cores to themselves: a caller whose
              own CPU work leaves spinning OpenMP threads behind (torch's intra-op pool after a small CPU op) should
              set OMP_WAIT_POLICY=passive or torch.set_num_threads(1).
     The step runs on the stepper's own stream; with follow_current_stream (default) it first waits for the work already

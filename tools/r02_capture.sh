@@ -27,3 +27,5 @@ python tools/kernel_ab.py --quick --out $O/kernel_ab_final.json > $O/kernel_ab_f
 cuobjdump -sass gymgo_b200/_lib/libgymgo_b200.so 2>/dev/null | grep -c ATOMS > $O/atoms_count.txt
 tail -c 300 $O/bench_s20.err $O/bench_default.err $O/bench_19.err
 ls -la $O | tail -20
+python tools/e2e_phases.py > $O/e2e_phases.json 2>> $O/bench_s20.err
+python tools/e2e_phases.py --size 19 --boards 16384 > $O/e2e_phases_19x19.json 2>> $O/bench_s20.err
