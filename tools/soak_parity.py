@@ -26,7 +26,8 @@ def main():
     target = float(sys.argv[1]) if len(sys.argv) > 1 else 4.0
     co.build()
     pool = mp.get_context("fork").Pool(min(16, os.cpu_count() or 1))
-    for n, boards in ((9, 32768), (19, 8192), (7, 32768), (13, 8192), (5, 32768), (3, 32768), (16, 4096)):
+    for n, boards in ((9, 65536), (9, 32768), (19, 16384), (8, 65536), (7, 65536), (13, 8192), (6, 65536), (5, 32768), (4, 65536),
+                      (3, 32768), (16, 4096)):     # 65,536 boards of side <= 9 select k_rollout_tpb, the rest k_rollout
         e = GoEngine(n, "cuda:0")
         chunk = 16
         rec = e.new_records(boards)
@@ -37,6 +38,7 @@ def main():
         t = 0
         t0 = time.time()
         want_total = int(target * 1e6 * (1.0 if n in (9, 19) else 0.25))
+        kernel = e.lib.gg_rollout_kernel(n, boards).decode()
         while done < want_total:
             e.rollout(rec, 20240925, 0, t, chunk, plies_per_launch=chunk, actions_log=acts, obs_ring=ring)
             obs = ring.cpu().numpy()
@@ -53,8 +55,8 @@ def main():
                 mismatches += mm
             done += chunk * boards
             t += chunk
-        print("N=%2d  %9d transitions  illegal-action batches %d  state mismatches %d  (%.1f s)"
-              % (n, done, bad_status, mismatches, time.time() - t0), flush=True)
+        print("N=%2d x %6d  %9d transitions  illegal-action batches %d  state mismatches %d  (%.1f s)  %s"
+              % (n, boards, done, bad_status, mismatches, time.time() - t0, kernel), flush=True)
         assert bad_status == 0 and mismatches == 0
     print("soak parity OK")
 
