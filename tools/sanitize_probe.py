@@ -19,6 +19,14 @@ for n, boards in ((9, 83), (19, 21), (7, 50), (5, 130)):
     e.rollout(rec, 1, 0, 0, 12, plies_per_launch=5, actions_log=acts, obs_ring=ring, done_log=done, reward_log=rew,
               reward_mode=2, komi=0.5)
     e.rollout(rec, 1, 0, 12, 7, plies_per_launch=7, obs_ring=ring8)
+    # both persistent kernels, static and dynamically scheduled ((tile, 2-ply) tickets), every observation dtype
+    ring16 = e.empty((3, boards, 6, n, n), dtype=torch.bfloat16)
+    for kernel in (0, 1):
+        for dyn in (False, True):
+            for r in (ring, ring8, ring16):
+                e.rollout(rec, 1, 0, 19, 9, plies_per_launch=9, actions_log=acts, obs_ring=r, done_log=done, reward_log=rew,
+                          reward_mode=1, kernel=kernel, dynamic=dyn, block_plies=2)
+    e.step(rec, e.sample_legal(rec, 2, 0, 5), out=rec, auto_reset=True, obs_dtype=torch.bfloat16)
     a = e.sample_legal(rec, 2, 0, 0)
     res = e.step(rec, a, obs_dtype=torch.float32, want_done=True, want_areas=True, reward_mode=1)
     res = e.step(res["rec"], e.sample_legal(res["rec"], 2, 0, 1), out=res["rec"], obs_dtype=torch.uint8)
