@@ -8,9 +8,13 @@
 //   2. every lane keeps its slice of the three bit-planes in registers and runs gg::Algo (floods are
 //      carry chains + neighbour shuffles, votes are ballots) - no shared-memory traffic in the rules;
 //   3. new records go back to shared memory and leave with one bulk async store;
-//   4. the dense [6,N,N] observation (what GoEnv.step returns) is produced from a per-tile bit stream in
-//      shared memory: each 16-byte store expands one nibble (f32) or 16 bits (u8) - fully coalesced
-//      128-bit stores, which is the HBM traffic that dominates the step.
+//   4. the dense [6,N,N] observation (what GoEnv.step returns) is produced from a bit stream in shared memory
+//      (per tile in k_step, per warp in the rollout kernels; assembled with atomicOr by the lane-sliced
+//      kernels, in registers + funnel shifts + one shuffle by the thread-per-board kernel): each 16-byte store
+//      expands one nibble (f32), one byte (bf16/f16) or 16 bits (u8) through a small table - fully coalesced
+//      128-bit streaming stores, which is the HBM traffic that dominates the step.
+// The persistent rollout kernels (k_rollout, k_rollout_tpb) keep the boards in registers over the plies of a work
+// item and are dynamically scheduled: (tile, 4-ply block) tickets, see RolloutArgs.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
