@@ -60,7 +60,7 @@ def algorithmic_bytes_per_ply(n, obs_bytes_per_elem):
 
 def profiled_traffic(size, obs, plies_in_launch):
     """DRAM bytes of one launch of the dominant kernel, scaled from the committed ncu capture of this configuration
-    (profiles/traffic.json: bytes per ply of a 32-ply launch) to the plies this run puts in a launch; None if no capture"""
+    (profiles/traffic.json: bytes per ply of a 128-ply launch) to the plies this run puts in a launch; None if no capture"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             row = json.load(f)["%dx%d/%s" % (size, size, obs)]
@@ -281,7 +281,8 @@ def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches,
     per_launch = boards * bytes_per_ply * plies_in_launch
     achieved = per_launch / launch_s / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": profiled_traffic(size, obs_name, plies_in_launch),
+            "traffic": (profiled_traffic(size, obs_name, plies_in_launch) or {}).get("dram_bytes_per_launch"),
+            "traffic_source": (profiled_traffic(size, obs_name, plies_in_launch) or {}).get("source"),
             "algorithmic_bytes_per_launch": per_launch, "plies_per_launch": plies_in_launch,
             "kernel": "gg::%s, Geo<%d>, dynamically scheduled in 4-ply blocks" % (
                 eng.lib.gg_rollout_kernel(size, boards).decode(), size),
@@ -292,7 +293,7 @@ def roofline_record(eng, boards, obs_elem, obs_name, k, secs, repeats, launches,
                         "run.  `peak` is the driver's measured COPY bandwidth, not the hardware limit (HBM3e nominal "
                         "~8 TB/s): frac > 1 means this kernel's store stream - every warp writing long contiguous runs - "
                         "sustains more than that copy and more than the plain fill; ncu confirms the bytes reach DRAM "
-                        "(`traffic` ~ algorithmic bytes, dram__cycles_active 85 % / 75 % in profiles/r02_k_rollout_*)"},
+                        "(`traffic` ~ algorithmic bytes, dram__cycles_active 86 % / 76 % in profiles/r02_final_k_rollout_*)"},
             "timing": "CUDA events on the launching stream around %d launches" % launches}
 
 
