@@ -14,6 +14,7 @@ GG_OK, GG_EINVAL, GG_ESIZE, GG_EALIGN, GG_ECUDA = 0, -1, -2, -3, -4
 GG_ST_OK, GG_ST_INVALID_MOVE, GG_ST_OUT_OF_RANGE, GG_ST_GAME_OVER = 0, 1, 2, 3
 GG_U8, GG_F32, GG_F64, GG_BF16, GG_F16 = 0, 1, 2, 3, 4
 GG_STEP_CANONICAL, GG_STEP_REFUSE_DONE, GG_STEP_AUTO_RESET, GG_STEP_RESET_SKIPS_ACTION = 1, 2, 4, 8
+GG_STEP_KERNEL_LANES, GG_STEP_KERNEL_THREAD = 16, 32
 GG_KERNEL_AUTO, GG_KERNEL_LANES, GG_KERNEL_THREAD = -1, 0, 1
 GG_VERSION = 200
 

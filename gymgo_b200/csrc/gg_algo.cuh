@@ -39,7 +39,8 @@ namespace gg {
 enum : uint32_t { FLAG_TURN = 1u, FLAG_PASS = 2u, FLAG_DONE = 4u };
 enum : int { ST_OK = 0, ST_INVALID_MOVE = 1, ST_OUT_OF_RANGE = 2, ST_GAME_OVER = 3 };
 // step option bits (also the `flags` argument of gg_step in include/gymgo_b200.h)
-enum : uint32_t { OPT_CANONICAL = 1u, OPT_REFUSE_DONE = 2u, OPT_AUTO_RESET = 4u, OPT_RESET_SKIPS_ACTION = 8u };
+enum : uint32_t { OPT_CANONICAL = 1u, OPT_REFUSE_DONE = 2u, OPT_AUTO_RESET = 4u, OPT_RESET_SKIPS_ACTION = 8u,
+                  OPT_KERNEL_LANES = 16u, OPT_KERNEL_THREAD = 32u };   // (kernel selectors: not rule options)
 
 constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 constexpr int default_wordbits(int n) { return n <= 9 ? 32 : 64; }

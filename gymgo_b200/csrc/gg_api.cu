@@ -118,7 +118,9 @@ GG_API int gg_step(const void* rec_in, const int32_t* actions, void* rec_out, ui
             int reward_mode, float komi, void* stream) {
     const SizeVTable* v = lookup(n);
     if (!v) return GG_ESIZE;
-    if (batch < 0 || (flags & ~(GG_STEP_CANONICAL | GG_STEP_REFUSE_DONE | GG_STEP_AUTO_RESET | GG_STEP_RESET_SKIPS_ACTION))) return GG_EINVAL;
+    if (batch < 0 || (flags & ~(GG_STEP_CANONICAL | GG_STEP_REFUSE_DONE | GG_STEP_AUTO_RESET | GG_STEP_RESET_SKIPS_ACTION |
+                                GG_STEP_KERNEL_LANES | GG_STEP_KERNEL_THREAD))) return GG_EINVAL;
+    if ((flags & GG_STEP_KERNEL_LANES) && (flags & GG_STEP_KERNEL_THREAD)) return GG_EINVAL;
     if (batch > 0 && (!rec_in || !rec_out || !actions)) return GG_EINVAL;
     if (obs_out && !dense_dtype_ok(obs_dtype, false)) return GG_EINVAL;
     if (reward_mode < GG_REWARD_NONE || reward_mode > GG_REWARD_HEURISTIC) return GG_EINVAL;

@@ -933,6 +933,126 @@ __global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k
     }
 }
 
+// =================================================================================================
+// Thread-per-board form of the single-ply STEP kernel (caller-provided actions): the host-driven path of small boards.
+// Same contract as k_step<G, MODE_STEP> (options, status, done / areas / reward outputs, refused boards untouched) and
+// bit-identical results; the rules run without shuffles or ballots (gg::ArrayOps, 153 instead of 206 warp-instructions
+// per 9x9 board-ply) and every warp expands the observation of ITS 32 boards from a warp-private stream - no CTA
+// barrier between the rules and the stores.
+// =================================================================================================
+template <class G>
+__global__ void __launch_bounds__(TpbTile<G>::THREADS, TpbTile<G>::MIN_BLOCKS) k_step_tpb(const StepArgs a) {
+    typedef TpbTile<G> T;
+    typedef ArrayOps<G> O;
+    typedef ArrayPlane<G> P;
+    __shared__ __align__(16) uint32_t s_rec[T::BT * G::REC_W32];
+    __shared__ uint32_t s_bits_all[T::THREADS / 32][T::WSTREAM_W32];
+    __shared__ __align__(16) float4 s_lut[LUT_F4];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile_base = (long long)blockIdx.x * T::BT;
+    const long long left = a.slots - tile_base;
+    const int nb = left < T::BT ? int(left) : T::BT;
+    const bool want_obs = a.obs != nullptr;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    if (want_obs) obs_lut_init<T::THREADS>(s_lut, a.obs_dtype, tid);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, uint32_t(nb) * G::REC_BYTES);
+        bulk_g2s(s_rec, a.rec_in + tile_base * G::REC_W32, uint32_t(nb) * G::REC_BYTES, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const bool real = tid < nb;
+    const long long slot = tile_base + tid;
+    const O o(real);
+    uint32_t* my_rec = s_rec + tid * G::REC_W32;
+    P black = o.zero(), white = o.zero(), invd = o.zero();
+    uint32_t flags = 0;
+    int action = G::NP;
+    bool restarted = false;
+    if (real) {
+#pragma unroll
+        for (int j = 0; j < G::LPB; ++j) {
+            black.w[j] = rec_word<G>(my_rec, 0, j);
+            white.w[j] = rec_word<G>(my_rec, 1, j);
+            invd.w[j] = rec_word<G>(my_rec, 2, j);
+        }
+        flags = my_rec[G::FLAGS_IDX];
+        action = a.actions_in[slot];
+        if ((a.opts & OPT_AUTO_RESET) && (flags & FLAG_DONE)) {       // a finished board restarts before its action
+            black = white = invd = o.zero();
+            flags = 0;
+            restarted = true;
+            if (a.opts & OPT_RESET_SKIPS_ACTION) action = -1;          // gymnasium next-step autoreset (refused below)
+        }
+    }
+    int status = Algo<O>::step(o, G(), black, white, invd, flags, action, a.opts);
+    if (restarted && (a.opts & OPT_RESET_SKIPS_ACTION)) status = ST_OK;    // fresh board, nothing played
+
+    const bool over = (flags & FLAG_DONE) != 0;
+    if (real) {
+        if (a.status) a.status[slot] = uint8_t(status);
+        if (a.done_out) a.done_out[slot] = over ? 1 : 0;
+        const bool want_reward = a.reward_out != nullptr;
+        if (a.areas_out != nullptr || (want_reward && (a.reward_mode == 2 || over))) {
+            int ba, wa;
+            Algo<O>::areas(o, black, white, ba, wa);
+            if (a.areas_out) {
+                a.areas_out[2 * slot] = ba;
+                a.areas_out[2 * slot + 1] = wa;
+            }
+            if (want_reward) {
+                const float diff = float(ba - wa) - a.komi;
+                float r;
+                if (a.reward_mode == 1) r = over ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+                else r = over ? (diff > 0.f ? float(G::NP) : -float(G::NP)) : diff;
+                a.reward_out[slot] = r;
+            }
+        } else if (want_reward) {
+            a.reward_out[slot] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < G::LPB; ++j) {                             // padding words of the record keep the input's
+            rec_word_store<G>(my_rec, 0, j, black.w[j]);
+            rec_word_store<G>(my_rec, 1, j, white.w[j]);
+            rec_word_store<G>(my_rec, 2, j, invd.w[j]);
+        }
+        my_rec[G::FLAGS_IDX] = flags;
+    }
+    fence_proxy_async();            // generic-proxy writes to s_rec must be visible to the bulk store
+    __syncthreads();
+    if (a.rec_out && tid == 0) {
+        bulk_s2g(a.rec_out + tile_base * G::REC_W32, s_rec, uint32_t(nb) * G::REC_BYTES);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (want_obs) {
+        uint32_t* s_bits = s_bits_all[warp];
+        int nbw = nb - warp * 32;
+        nbw = nbw < 0 ? 0 : (nbw > 32 ? 32 : nbw);
+        const long long abs0 = (tile_base + warp * 32) * T::DENSE;    // this warp's first element of the dense output
+        const int head = int(abs0 & obs_align_mask(a.obs_dtype));
+        if constexpr (TpbStream<G>::SHUFFLED) {
+            tpb_stream_put<G>(s_bits, head + lane * T::DENSE, lane, real, black, white, invd, flags);
+        } else {
+            for (int i = lane; i < T::WSTREAM_W32; i += 32) s_bits[i] = 0;
+            __syncwarp();
+            if (real) {
+#pragma unroll
+                for (int j = 0; j < G::LPB; ++j)
+                    stream_put_board<G>(s_bits, head + lane * T::DENSE, j, black.w[j], white.w[j], invd.w[j], flags);
+            }
+        }
+        __syncwarp();
+        emit_obs<32>(a.obs_dtype, s_bits, s_lut, head, nbw * T::DENSE, a.obs, abs0 - head, lane);
+    }
+    if (a.rec_out && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 inline unsigned blocks_for(long long items, int per_block) { return unsigned((items + per_block - 1) / per_block); }
 
 // fills in the dynamic-scheduling fields for tiles of `tile_boards` boards; -> CTAs to launch
@@ -1201,10 +1321,23 @@ struct SizeVTable {
 
 template <class G>
 struct Launch {
+    // which STEP kernel: an explicit choice (GG_STEP_KERNEL_*), else thread-per-board for small boards (uint32 words,
+    // <= 3 words per plane) in large batches (>= 48 Ki boards) unless a float32 observation is written.  Measured on
+    // 9x9 x 65,536 (tools/kstep_phase_probe.py, us per launch, lanes -> thread): no observation 17.0 -> 15.2, u8
+    // 20.6 -> 17.3, bf16 21.9 -> 18.9, f32 28.9 -> 29.3 (store-bound: the CTA-wide emission of k_step is as good).
+    static bool step_uses_thread_kernel(const StepArgs& a) {
+        if (a.opts & OPT_KERNEL_THREAD) return true;
+        if (a.opts & OPT_KERNEL_LANES) return false;
+        return G::WB == 32 && G::LPB <= 3 && a.slots >= 49152 && !(a.obs != nullptr && a.obs_dtype == DT_F32);
+    }
     static cudaError_t step(const StepArgs& a, int mode, cudaStream_t s) {
         if (a.slots <= 0) return cudaSuccess;
         const unsigned grid = blocks_for(a.slots, Tile<G>::BT);
-        if (mode == MODE_STEP) k_step<G, MODE_STEP><<<grid, Tile<G>::THREADS, 0, s>>>(a);
+        if (mode == MODE_STEP && step_uses_thread_kernel(a)) {
+            StepArgs b = a;
+            b.opts &= ~(OPT_KERNEL_LANES | OPT_KERNEL_THREAD);
+            k_step_tpb<G><<<blocks_for(a.slots, TpbTile<G>::BT), TpbTile<G>::THREADS, 0, s>>>(b);
+        } else if (mode == MODE_STEP) k_step<G, MODE_STEP><<<grid, Tile<G>::THREADS, 0, s>>>(a);
         else if (mode == MODE_ROLLOUT) k_step<G, MODE_ROLLOUT><<<grid, Tile<G>::THREADS, 0, s>>>(a);
         else k_step<G, MODE_CHILDREN><<<grid, Tile<G>::THREADS, 0, s>>>(a);
         return cudaGetLastError();

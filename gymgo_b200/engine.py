@@ -128,10 +128,13 @@ class GoEngine(object):
 
     # ------------------------------------------------------------------ the hot path
     def step(self, rec, actions, out=None, canonical=False, refuse_done=False, obs=None, obs_dtype=None,
-             want_status=True, want_done=False, want_areas=False, reward_mode=0, komi=0.0, auto_reset=False):
+             want_status=True, want_done=False, want_areas=False, reward_mode=0, komi=0.0, auto_reset=False,
+             kernel=None):
         """One ply per board.  Returns dict(rec, status, obs, done, areas, reward) of device tensors
         (entries not asked for are None).  `out=rec` steps in place.  auto_reset: boards whose record is finished
-        restart from the empty position before playing their action (GG_STEP_AUTO_RESET)."""
+        restart from the empty position before playing their action (GG_STEP_AUTO_RESET); auto_reset="skip" also
+        ignores their action for this ply (GG_STEP_RESET_SKIPS_ACTION).  kernel: None (chosen by the library),
+        "lanes" or "thread" (GG_STEP_KERNEL_*; identical results)."""
         self._check_rec(rec)
         b = rec.shape[0]
         a = self._actions(actions, b)
@@ -149,7 +152,9 @@ class GoEngine(object):
         areas = self.empty((b, 2), dtype=torch.int32) if want_areas else None
         reward = self.empty((b,), dtype=torch.float32) if reward_mode else None
         flags = (_cabi.GG_STEP_CANONICAL if canonical else 0) | (_cabi.GG_STEP_REFUSE_DONE if refuse_done else 0) \
-            | (_cabi.GG_STEP_AUTO_RESET if auto_reset else 0)
+            | (_cabi.GG_STEP_AUTO_RESET if auto_reset else 0) \
+            | (_cabi.GG_STEP_RESET_SKIPS_ACTION if auto_reset == "skip" else 0) \
+            | {None: 0, "lanes": _cabi.GG_STEP_KERNEL_LANES, "thread": _cabi.GG_STEP_KERNEL_THREAD}[kernel]
         s = self._enter()
         _cabi.check(self.lib.gg_step(_ptr(rec), _ptr(a), _ptr(out), _ptr(status), b, self.size, flags, _ptr(obs),
                                      _TORCH2GG[obs.dtype] if obs is not None else 0, _ptr(done), _ptr(areas),

@@ -75,6 +75,12 @@ extern "C" {
 #define GG_STEP_RESET_SKIPS_ACTION 8u /* with GG_STEP_AUTO_RESET: a board that was just reset does NOT play its action
                                        * this ply (status OK, empty board out) - gymnasium's next-step autoreset */
 
+/* gg_step only: which single-ply kernel runs.  Default (neither bit): chosen from measurements like the rollout kernels -
+ * thread-per-board for uint32 boards (n <= 9) in batches of >= 48 Ki when no float32 observation is written (12-16 %
+ * faster there), lane-sliced otherwise.  Results are identical. */
+#define GG_STEP_KERNEL_LANES 16u  /* k_step: a board spread over adjacent lanes of a warp */
+#define GG_STEP_KERNEL_THREAD 32u /* k_step_tpb: one board per thread */
+
 /* rollout kernels (gg_rollout_with); both produce identical results */
 #define GG_KERNEL_AUTO (-1)    /* chosen per (n, batch) from measurements: what gg_rollout uses */
 #define GG_KERNEL_LANES 0      /* k_rollout: a board spread over adjacent lanes of a warp */

@@ -59,7 +59,9 @@ def test_rollout_kernel_choice_and_new_argument_checks():
     small_ws = lib.gg_rollout_with(0, addr, 4096, 9, 0, 0, 0, 32, 32, None, None, 0, 0, None, None, 0, 0.0, addr, 16, 0, None)
     assert small_ws == _cabi.GG_EINVAL                                   # workspace too small for the batch
     assert lib.gg_rollout_with(0, addr, 4, 9, 0, 0, 0, 3, 1, None, None, 0, 0, None, None, 0, 0.0, None, 0, -1, None) == _cabi.GG_EINVAL
-    assert lib.gg_step(addr, addr, addr, None, 4, 9, 16, None, 0, None, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
+    assert lib.gg_step(addr, addr, addr, None, 4, 9, 64, None, 0, None, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
+    both = _cabi.GG_STEP_KERNEL_LANES | _cabi.GG_STEP_KERNEL_THREAD                      # contradictory kernel choice
+    assert lib.gg_step(addr, addr, addr, None, 4, 9, both, None, 0, None, None, None, 0, 0.0, None) == _cabi.GG_EINVAL
     assert lib.gg_update_pieces(addr, addr, addr, addr, 4, 9, None) == _cabi.GG_EINVAL       # killed aliases rec
     assert lib.gg_update_pieces(None, addr, addr, addr, 4, 9, None) == _cabi.GG_EINVAL
     assert lib.gg_host_unpack(None, 4, 9, 1, addr, 1) == _cabi.GG_EINVAL

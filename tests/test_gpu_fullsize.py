@@ -87,6 +87,31 @@ def test_deep_rollout_soak_against_c_oracle(n, boards, kernel_name):
     invariants(e.unpack(rec, dtype=torch.uint8).cpu().numpy())
 
 
+def test_headline_batch_step_kernel_choice_against_c_oracle():
+    """BatchedGoEnv.step at the headline batch (9x9 x 65,536: gg_step picks k_step_tpb by itself) along 200 plies of a
+    game with auto-reset: the same records as the lane-sliced kernel driven with the same actions, and a strided sample
+    of every ply replayed through the C oracle (next state, status, done)"""
+    from gymgo_b200.engine import GoEngine
+    n, boards = 9, 65536
+    e = GoEngine(n, "cuda:0")
+    auto, lanes = e.new_records(boards), e.new_records(boards)
+    obs = e.empty((boards, 6, n, n), dtype=torch.uint8)
+    sample = torch.arange(0, boards, 128, device="cuda")
+    for t in range(200):
+        acts = e.sample_legal(auto, 21, 0, t)
+        if t % 7 == 3:
+            acts[::50] = n * n + 5                                           # a few out-of-range actions
+        before = e.unpack(auto[sample], dtype=torch.uint8).cpu().numpy()
+        ra = e.step(auto, acts, out=auto, obs=obs, auto_reset=True, want_done=True)
+        rl = e.step(lanes, acts, out=lanes, auto_reset=True, want_done=True, kernel="lanes")
+        assert torch.equal(auto, lanes) and torch.equal(ra["status"], rl["status"]) and torch.equal(ra["done"], rl["done"])
+        before[before[:, 5, 0, 0] == 1] = 0                                   # auto-reset precedes the ply
+        want, wstatus = co.batch_next_states(before, acts[sample].cpu().numpy())
+        assert np.array_equal(obs[sample].cpu().numpy(), want), t
+        assert np.array_equal(ra["status"][sample].cpu().numpy(), wstatus), t
+    assert bool((e.flags(auto) & 4).any())
+
+
 def test_children_full_config():
     """configs[3]: 9x9 children() of 4,096 parents after 40 random plies; every slot against per-action gg_step,
     a sample against the C oracle."""

@@ -43,8 +43,11 @@ def test_layout_and_codec_roundtrip(eng, n):
         assert back.dtype == dt and np.array_equal(back.cpu().numpy().astype(np.uint8), st)
 
 
+@pytest.mark.parametrize("kernel", ("lanes", "thread"))
 @pytest.mark.parametrize("n", ALL_SIZES)
-def test_step_vs_oracle_on_soup(eng, n):
+def test_step_vs_oracle_on_soup(eng, n, kernel):
+    """gg_step against the C oracle on random positions incl. refused moves, for BOTH single-ply kernels
+    (k_step: lane-sliced boards; k_step_tpb: one board per thread)"""
     e = eng(n)
     count = 4001 if n <= 9 else 1203
     rng = np.random.RandomState(500 + n)
@@ -57,14 +60,14 @@ def test_step_vs_oracle_on_soup(eng, n):
     rec = e.pack(dev(st))
     for canon in (False, True):
         want, wstatus = co.batch_next_states(st, acts, canon)
-        res = e.step(rec, acts, canonical=canon, obs_dtype=torch.uint8, want_done=True, want_areas=True)
+        res = e.step(rec, acts, canonical=canon, obs_dtype=torch.uint8, want_done=True, want_areas=True, kernel=kernel)
         assert np.array_equal(res["status"].cpu().numpy(), wstatus)
         assert np.array_equal(e.unpack(res["rec"], dtype=torch.uint8).cpu().numpy(), want)
         assert np.array_equal(res["obs"].cpu().numpy(), want)                     # fused observation
         assert np.array_equal(res["done"].cpu().numpy(), want[:, 5, 0, 0])
         assert np.array_equal(res["areas"].cpu().numpy(), co.batch_areas(want))
     # refuse_done option
-    res = e.step(rec, acts, refuse_done=True)
+    res = e.step(rec, acts, refuse_done=True, kernel=kernel)
     done = st[:, 5, 0, 0] == 1
     got = res["status"].cpu().numpy()
     assert (got[done & (acts >= 0) & (acts <= n * n)] == 3).all()
@@ -94,22 +97,52 @@ def test_golden_soup(eng, n):
     assert np.array_equal(e.areas(e.pack(dev(S0))).cpu().numpy(), AR.astype(np.int32))
 
 
+@pytest.mark.parametrize("kernel", ("lanes", "thread"))
 @pytest.mark.parametrize("n", (3, 7, 9, 19))
 @pytest.mark.parametrize("batch", (1, 7, 39, 41, 130, 1000))
 @pytest.mark.parametrize("dtype", (torch.float32, torch.uint8, torch.bfloat16, torch.float16))
-def test_obs_emission_tail_tiles(eng, n, batch, dtype):
-    """the fused dense output equals the independent unpack kernel for ragged batch sizes"""
+def test_obs_emission_tail_tiles(eng, n, batch, dtype, kernel):
+    """the fused dense output equals the independent unpack kernel for ragged batch sizes (both single-ply kernels)"""
     e = eng(n)
     st = soup(n, batch, 9000 + n + batch)
     st[:, 5] = 0
     rec = e.pack(dev(st))
     acts = e.sample_legal(rec, 3, 0, 0)
     guard = torch.full((batch + 1, 6, n, n), 7, dtype=dtype, device="cuda")      # one extra board as canary
-    res = e.step(rec, acts, obs=guard[:batch])
+    res = e.step(rec, acts, obs=guard[:batch], kernel=kernel)
     assert torch.equal(res["obs"], e.unpack(res["rec"], dtype=dtype))
     assert torch.equal(res["obs"].float(), e.unpack(res["rec"], dtype=torch.float32))
     assert bool((guard[batch] == 7).all())                                          # nothing written past the end
     assert torch.equal(e.pack(res["obs"]), res["rec"])                              # and it packs back to the record
+
+
+@pytest.mark.parametrize("n,boards", ((9, 2500), (8, 100), (6, 777), (5, 64), (4, 65), (3, 31), (2, 200), (13, 97), (19, 75)))
+def test_step_kernels_are_bit_identical_for_every_option(eng, n, boards):
+    """k_step (lane-sliced) and k_step_tpb (one board per thread) agree on records, status, observation, done, areas and
+    rewards for every option of gg_step - canonical, refuse-done, auto-reset, reset-skips-action, both reward modes -
+    along games that contain finished boards, refused and out-of-range actions; in-place and out-of-place"""
+    e = eng(n)
+    rec = e.new_records(boards)
+    e.rollout(rec, 3, 0, 0, 3 * n * n, plies_per_launch=16)               # mixed game phases incl. finished boards
+    rng = np.random.RandomState(n)
+    combos = [dict(), dict(canonical=True), dict(refuse_done=True), dict(auto_reset=True, refuse_done=True),
+              dict(auto_reset="skip", refuse_done=True), dict(auto_reset=True, canonical=True)]
+    a_rec, b_rec = rec.clone(), rec.clone()
+    for t in range(40):
+        acts = e.sample_legal(a_rec, 11, 0, t)
+        bad = torch.from_numpy(rng.uniform(size=boards) < 0.15).cuda()
+        junk = torch.from_numpy(rng.randint(-2, n * n + 3, size=boards).astype(np.int32)).cuda()
+        acts = torch.where(bad, junk, acts)                                  # illegal / out-of-range actions in the mix
+        opt = combos[t % len(combos)]
+        dt = (torch.float32, torch.uint8, torch.bfloat16)[t % 3]
+        kw = dict(obs_dtype=dt, want_done=True, want_areas=(t % 2 == 0), reward_mode=1 + t % 2, komi=0.5, **opt)
+        ra = e.step(a_rec, acts, out=a_rec if t % 4 else None, kernel="lanes", **kw)
+        rb = e.step(b_rec, acts, out=b_rec if t % 4 else None, kernel="thread", **kw)
+        for key in ("rec", "status", "obs", "done", "areas", "reward"):
+            assert (ra[key] is None) == (rb[key] is None), key
+            if ra[key] is not None:
+                assert torch.equal(ra[key], rb[key]), (t, key, opt)
+        a_rec, b_rec = ra["rec"], rb["rec"]
 
 
 @pytest.mark.parametrize("n,boards,steps", ((5, 333, 120), (9, 1000, 260), (13, 200, 200), (19, 150, 300)))
