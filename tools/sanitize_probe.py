@@ -27,6 +27,10 @@ for n, boards in ((9, 83), (19, 21), (7, 50), (5, 130)):
                 e.rollout(rec, 1, 0, 19, 9, plies_per_launch=9, actions_log=acts, obs_ring=r, done_log=done, reward_log=rew,
                           reward_mode=1, kernel=kernel, dynamic=dyn, block_plies=2)
     e.step(rec, e.sample_legal(rec, 2, 0, 5), out=rec, auto_reset=True, obs_dtype=torch.bfloat16)
+    for kernel in ("lanes", "thread"):                      # both single-ply kernels, every output
+        for dt in (torch.float32, torch.uint8, torch.float16):
+            e.step(rec, e.sample_legal(rec, 2, 0, 6), out=rec, auto_reset="skip", obs_dtype=dt, want_done=True, want_areas=True,
+                   reward_mode=2, komi=0.5, kernel=kernel)
     a = e.sample_legal(rec, 2, 0, 0)
     res = e.step(rec, a, obs_dtype=torch.float32, want_done=True, want_areas=True, reward_mode=1)
     res = e.step(res["rec"], e.sample_legal(res["rec"], 2, 0, 1), out=res["rec"], obs_dtype=torch.uint8)
